@@ -1,0 +1,30 @@
+"""Locate the (unmodified) Brian2 front-end the ``b200`` device plugs into.
+
+The device is a *plugin*: equations, ``NeuronGroup``/``Synapses``/monitors, ``Synapses.connect``
+and the state updaters are Brian2's own (BASELINE.json north_star).  If ``brian2`` is not
+already importable, fall back to the scripted install under ``oracle/_ref`` (see
+``oracle/install_ref.py``; git-ignored, travels to the GPU box with the snapshot).
+"""
+import importlib.util
+import os
+import sys
+
+REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(REPO_ROOT, "oracle", "_ref")
+
+
+def ensure_brian2_importable():
+    if "brian2" in sys.modules:
+        return
+    if importlib.util.find_spec("brian2") is not None:
+        return
+    if os.path.isdir(os.path.join(REF_DIR, "brian2")):
+        sys.path.insert(0, REF_DIR)
+        # host-side C++ (synapse creation etc.) must be built with a g++ that can link OpenMP
+        os.environ.setdefault("CXX", "/usr/bin/g++")
+        os.environ.setdefault("CC", "/usr/bin/gcc")
+        return
+    raise ImportError(
+        "brian2 is not importable and oracle/_ref is not populated; run "
+        "`python oracle/install_ref.py` (needs /root/reference) or install brian2"
+    )

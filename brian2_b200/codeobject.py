@@ -1,0 +1,132 @@
+"""Code object classes of the ``b200`` device.
+
+* `B200CodeObject` -- in-loop code objects, rendered from the CUDA templates in
+  ``brian2_b200/templates`` by `CUDACodeGenerator`.
+* `B200HostCodeObject` -- run-once code objects (variable initialisation, ``Synapses.connect``):
+  these stay *host C++ exactly as the reference emits them* (same templates, same
+  ``RandomGenerator``/mt19937 stream, ``templates/objects.cpp:426-479``), so connectivity and
+  initial state are bit-identical to ``cpp_standalone`` for the same ``seed()``.
+
+Pattern: ``brian2/devices/cpp_standalone/codeobject.py:85-172``.
+"""
+from brian2.codegen.codeobject import constant_or_scalar as host_constant_or_scalar
+from brian2.codegen.generators.cpp_generator import CPPCodeGenerator, c_data_type
+from brian2.codegen.targets import codegen_targets
+from brian2.codegen.templates import Templater
+from brian2.core.functions import DEFAULT_FUNCTIONS
+from brian2.core.preferences import prefs
+from brian2.devices.cpp_standalone.codeobject import CPPStandaloneCodeObject
+from brian2.devices.device import get_device
+
+from .cuda_generator import CUDACodeGenerator
+
+__all__ = ["B200CodeObject", "B200HostCodeObject", "DEVICE_TEMPLATES", "HOST_TEMPLATES"]
+
+#: templates that run inside the time loop and have a CUDA version
+DEVICE_TEMPLATES = {
+    "stateupdate",
+    "threshold",
+    "reset",
+    "synapses",
+    "synapses_push_spikes",
+    "spikemonitor",
+    "statemonitor",
+    "ratemonitor",
+}
+
+#: templates that only ever run once, on the host, before/between runs
+HOST_TEMPLATES = {
+    "group_variable_set",
+    "group_variable_set_conditional",
+    "synapses_create_generator",
+    "synapses_create_array",
+}
+
+
+def device_constant_or_scalar(varname, variable):
+    """Device flavour of ``codegen/codeobject.py:32``: scalar arrays are read through the
+    local device pointer of the code object."""
+    if variable.array:
+        return f"_ptr{get_device().get_array_name(variable)}[0]"
+    return f"{varname}"
+
+
+def b200_field(var):
+    """Name of the field of the device array table ``_A`` that holds ``var``."""
+    return get_device().arrays[var]
+
+
+class _DualTemplater(Templater):
+    """CUDA templates of this package first, the reference's C++ templates as fallback.
+    (`Templater.derive`, codegen/templates.py:152, cannot mix file extensions.)  The fallback is
+    only used to *look up* run-once templates -- `B200Device.code_object` re-routes those to
+    `B200HostCodeObject`."""
+
+    def __getattr__(self, item):
+        try:
+            return self.templates.get_template(item)
+        except KeyError:
+            try:
+                return getattr(CPPStandaloneCodeObject.templater, item)
+            except AttributeError as ex:
+                raise AttributeError(item) from ex
+
+
+class B200CodeObject(CPPStandaloneCodeObject):
+    """In-loop code object: a ``__device__`` function + kernel for sm_100a."""
+
+    templater = _DualTemplater(
+        "brian2_b200",
+        ".cu",
+        env_globals={
+            "c_data_type": c_data_type,
+            "constant_or_scalar": device_constant_or_scalar,
+            "b200_host_constant_or_scalar": host_constant_or_scalar,
+            "b200_field": b200_field,
+            "prefs": prefs,
+            "zip": zip,
+        },
+    )
+    generator_class = CUDACodeGenerator
+
+
+class B200HostCodeObject(CPPStandaloneCodeObject):
+    """Run-once host code object: the reference's own C++ templates and generator."""
+
+    templater = CPPStandaloneCodeObject.templater
+    generator_class = CPPCodeGenerator
+
+
+codegen_targets.add(B200CodeObject)
+codegen_targets.add(B200HostCodeObject)
+
+# ---------------------------------------------------------------------------------------------
+# Function implementations for device code.  Everything that is a plain libm call is inherited
+# from the C++ generator through the MRO lookup (core/functions.py:352-390); helpers that the
+# reference pastes as host-only support code (cpp_generator.py:603-656) live in
+# csrc/b200_functions.cuh instead and only need their name registered here.
+# ---------------------------------------------------------------------------------------------
+for _func, _name in [
+    ("exprel", "_exprel"),
+    ("abs", "_brian_abs"),
+    ("clip", "_clip"),
+    ("sign", "_sign"),
+    ("timestep", "_timestep"),
+    ("int", "_b200_int"),
+]:
+    DEFAULT_FUNCTIONS[_func].implementations.add_implementation(
+        CUDACodeGenerator, code=None, name=_name
+    )
+
+# In-loop random numbers: counter-based Philox streams (csrc/b200_runtime.cuh); the templates
+# create the per-element generator `_rng`.
+DEFAULT_FUNCTIONS["rand"].implementations.add_implementation(
+    B200CodeObject,
+    code={"support_code": "", "hashdefine_code": "#define _rand(_i) b200::rng_uniform(_rng)"},
+    name="_rand",
+)
+DEFAULT_FUNCTIONS["randn"].implementations.add_implementation(
+    B200CodeObject,
+    code={"support_code": "", "hashdefine_code": "#define _randn(_i) b200::rng_normal(_rng)"},
+    name="_randn",
+)

@@ -1,0 +1,723 @@
+"""The ``b200`` simulation device: ``set_device('b200')`` beside ``runtime``/``cpp_standalone``.
+
+Implements Brian2's ``Device`` plugin surface (``brian2/devices/device.py:86``) by deriving from
+``CPPStandaloneDevice`` (``brian2/devices/cpp_standalone/device.py:144``), as the reference's
+developer documentation recommends for new standalone back-ends
+(``docs_sphinx/developer/devices.rst:22-26``).  What is inherited: array bookkeeping and the array
+cache, ``main_queue``, run-argument handling, result files.  What is new:
+
+* run-once code objects stay reference host C++ (bit-identical initialisation / connectivity),
+  in-loop code objects become sm_100a ``__device__`` functions (`B200CodeObject`);
+* the project is built into ONE shared library with ``nvcc`` and driven in-process through the
+  C ABI of ``include/brian2_b200.h`` (ctypes) instead of ``subprocess.call(['./main'])``;
+* every ``run()`` call gets a *persistent step kernel*: the schedule of code objects is known at
+  build time, so the device computes where grid barriers are really needed from the code
+  objects' read/write sets (``_plan_barriers``) and emits a cooperative kernel that executes the
+  whole time loop on the GPU.
+"""
+import os
+import shutil
+import sys
+import tempfile
+import time
+from collections import defaultdict
+
+import numpy as np
+
+from brian2.codegen.generators.cpp_generator import c_data_type
+from brian2.core.namespace import get_local_namespace
+from brian2.core.preferences import BrianPreference, prefs
+from brian2.core.variables import ArrayVariable, Constant, DynamicArrayVariable
+from brian2.devices.cpp_standalone.codeobject import CPPStandaloneCodeObject
+from brian2.devices.cpp_standalone.device import CPPStandaloneDevice
+from brian2.devices.device import all_devices
+from brian2.parsing.rendering import CPPNodeRenderer
+from brian2.units import second
+from brian2.utils.logger import get_logger
+
+from .capi import B200Library
+from .codeobject import (
+    DEVICE_TEMPLATES,
+    HOST_TEMPLATES,
+    B200CodeObject,
+    B200HostCodeObject,
+)
+from .cuda_generator import clock_field, is_eventspace
+
+__all__ = ["B200Device", "b200_device"]
+
+logger = get_logger("brian2.devices.b200")
+
+PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PACKAGE_DIR, "csrc")
+INCLUDE_DIR = os.path.join(os.path.dirname(PACKAGE_DIR), "include")
+
+prefs.register_preferences(
+    "devices.b200",
+    "B200 (sm_100a) standalone device preferences",
+    nvcc=BrianPreference(
+        default=os.environ.get("B200_NVCC", "/usr/local/cuda/bin/nvcc"),
+        docs="The nvcc binary used to compile the device code.",
+    ),
+    cuda_home=BrianPreference(
+        default=os.environ.get("CUDA_HOME", "/usr/local/cuda"), docs="CUDA toolkit root."
+    ),
+    arch_flags=BrianPreference(
+        default="-gencode arch=compute_100a,code=sm_100a",
+        docs="Target architecture flags passed to nvcc (Blackwell B200 only).",
+    ),
+    fmad=BrianPreference(
+        default=False,
+        docs="""
+        Allow nvcc to contract a*b+c into fused multiply-adds in device code.  Off by default so
+        that results are bit-comparable with a C++ build compiled with ``-ffp-contract=off``.
+        """,
+    ),
+    extra_nvcc_flags=BrianPreference(
+        default=["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-w"],
+        docs="Additional flags for nvcc.",
+    ),
+    persistent=BrianPreference(
+        default=True,
+        docs="""
+        Run the whole time loop inside one persistent cooperative kernel whenever all code objects
+        of a run share one regular clock.  If False, every code object is launched as its own
+        kernel every step (also used when profiling).
+        """,
+    ),
+    max_chunk=BrianPreference(
+        default=20000, docs="Maximum number of time steps per persistent-kernel launch."
+    ),
+    ctas_per_sm=BrianPreference(
+        default=2, docs="Resident CTAs (512 threads each) per SM used to size all grids."
+    ),
+    grid=BrianPreference(
+        default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
+    ),
+)
+
+
+class _SubprocessShim:
+    """Stands in for the ``subprocess`` module inside ``CPPStandaloneDevice.run`` so that the
+    inherited run-argument handling is reused while the project is executed in-process."""
+
+    def __init__(self, runner):
+        self._runner = runner
+
+    def call(self, cmd, stdout=None, **kwds):
+        return self._runner(cmd, stdout)
+
+
+class B200Device(CPPStandaloneDevice):
+    """Brian2 device that runs the per-timestep hot loop on one NVIDIA B200 (sm_100a)."""
+
+    def __init__(self):
+        super().__init__()
+        #: access summary (read / write / scattered) of every device code object
+        self._b200_access = {}
+        #: extra information recorded when a code object is created
+        self._b200_info = {}
+        #: one entry per `Network.run` call: list of (clock, codeobj)
+        self._b200_plans = []
+        self._b200_stream_counter = 0
+        self._b200_seed = None
+        self._b200_library = None
+        self._b200_run_counter = 0
+        self.cu_source_files = []
+
+    # ------------------------------------------------------------------------------------------
+    # code objects
+    # ------------------------------------------------------------------------------------------
+    def code_object_class(self, codeobj_class=None, fallback_pref=None):
+        if codeobj_class is None:
+            return B200CodeObject
+        return codeobj_class
+
+    def code_object(
+        self,
+        owner,
+        name,
+        abstract_code,
+        variables,
+        template_name,
+        variable_indices,
+        codeobj_class=None,
+        template_kwds=None,
+        override_conditional_write=None,
+        compiler_kwds=None,
+    ):
+        if template_name in HOST_TEMPLATES:
+            codeobj_class = B200HostCodeObject
+        elif template_name in DEVICE_TEMPLATES:
+            codeobj_class = B200CodeObject
+        else:
+            raise NotImplementedError(
+                f"The b200 device has no CUDA template for '{template_name}' code objects yet."
+            )
+        template_kwds = dict(template_kwds) if template_kwds is not None else {}
+        if codeobj_class is B200CodeObject:
+            self._b200_stream_counter += 1
+            clock = getattr(owner, "clock", None)
+            template_kwds["b200_clock"] = clock.name if clock is not None else "defaultclock"
+            template_kwds["b200_stream_id"] = self._b200_stream_counter
+            template_kwds["b200_template_name"] = template_name
+        codeobj = super().code_object(
+            owner,
+            name,
+            abstract_code,
+            variables,
+            template_name,
+            variable_indices,
+            codeobj_class=codeobj_class,
+            template_kwds=template_kwds,
+            override_conditional_write=override_conditional_write,
+            compiler_kwds=compiler_kwds,
+        )
+        if codeobj_class is B200CodeObject:
+            self._b200_info[codeobj.name] = {
+                "template": template_name,
+                "owner": owner,
+                "template_kwds": template_kwds,
+            }
+        return codeobj
+
+    def is_device_codeobj(self, codeobj):
+        return isinstance(codeobj, B200CodeObject)
+
+    # ------------------------------------------------------------------------------------------
+    # seed
+    # ------------------------------------------------------------------------------------------
+    def seed(self, seed=None):
+        super().seed(seed)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(7), "little")
+        # device RNG streams (in-loop rand/randn) are keyed on the same seed
+        self.main_queue.append(
+            ("insert_code", f"b200::state().seed = {int(seed)}ULL; b200::state().seeded = true;")
+        )
+
+    # ------------------------------------------------------------------------------------------
+    # run(): record the schedule of this run as a plan for a persistent kernel
+    # ------------------------------------------------------------------------------------------
+    def network_run(
+        self,
+        net,
+        duration,
+        report=None,
+        report_period=10 * second,
+        namespace=None,
+        profile=None,
+        level=0,
+        **kwds,
+    ):
+        if namespace is None:
+            namespace = get_local_namespace(level=level + 2)
+        build_on_run = self.build_on_run
+        self.build_on_run = False
+        try:
+            super().network_run(
+                net,
+                duration,
+                report=report,
+                report_period=report_period,
+                namespace=namespace,
+                profile=profile,
+                level=level + 1,
+                **kwds,
+            )
+        finally:
+            self.build_on_run = build_on_run
+        # attach the plan to the generated `net.run(...)` line
+        # (after_run code objects may have been queued behind it: search backwards)
+        run_lines = None
+        for func, args in reversed(self.main_queue):
+            if func == "run_network" and args[0] is net:
+                run_lines = args[1]
+                break
+        assert run_lines is not None
+        # schedule of this run in execution order, recovered from the generated
+        # `net.add(&clock, _run_<codeobj>);` lines (the objects' code-object lists are cleared
+        # again by net.after_run())
+        import re as _re
+
+        clocks_by_name = {clock.name: clock for clock in self.clocks}
+        entries = []
+        for line in run_lines:
+            m = _re.match(rf"\s*{_re.escape(net.name)}\.add\(&(\w+), _run_(\w+)\);", line)
+            if m and m.group(2) in self.code_objects:
+                entries.append((clocks_by_name[m.group(1)], self.code_objects[m.group(2)]))
+        plan_index = len(self._b200_plans)
+        self._b200_plans.append(entries)
+        run_call = f"{net.name}.run("
+        for i, line in enumerate(run_lines):
+            if line.startswith(run_call) and line.rstrip().endswith(");"):
+                run_lines[i] = line.rstrip()[:-2] + f", &_b200_plan_{plan_index});"
+        if self.build_on_run:
+            if self.has_been_run:
+                raise RuntimeError(
+                    "The network has already been built and run before. Use set_device with "
+                    "build_on_run=False and an explicit device.build call to use multiple run "
+                    "statements with this device."
+                )
+            self.build(direct_call=False, **self.build_options)
+
+    # ------------------------------------------------------------------------------------------
+    # barrier analysis
+    # ------------------------------------------------------------------------------------------
+    def _codeobj_access(self, codeobj):
+        """Sets of array names: private (owned-partition) reads/writes and shared reads/writes."""
+        info = self._b200_info[codeobj.name]
+        acc = self._b200_access.get(
+            codeobj.name,
+            {"read": set(), "write": set(), "scattered_read": set(), "scattered_write": set()},
+        )
+        template = info["template"]
+        kw = info["template_kwds"]
+        owned = template in ("stateupdate", "threshold")
+        priv_r = set(acc["read"]) if owned else set()
+        priv_w = set(acc["write"]) if owned else set()
+        shared_r = set(acc["scattered_read"]) | (set() if owned else set(acc["read"]))
+        shared_w = set(acc["scattered_write"]) | (set() if owned else set(acc["write"]))
+        name_of = lambda var: self.get_array_name(var, access_data=False)
+        es = kw.get("eventspace_variable")
+        tmpl = getattr(codeobj.templater, template)
+        for varname in tmpl.writes_read_only:
+            if varname in codeobj.variables and isinstance(codeobj.variables[varname], ArrayVariable):
+                shared_w.add(name_of(codeobj.variables[varname]))
+        if template == "threshold":
+            shared_w.add(name_of(es))
+            if kw.get("_uses_refractory"):
+                priv_w.add(name_of(codeobj.variables["not_refractory"]))
+                priv_w.add(name_of(codeobj.variables["lastspike"]))
+        elif template in ("reset", "spikemonitor", "synapses"):
+            if es is None and template == "synapses":
+                es = kw["pathway"].variables[kw["pathway"].eventspace_name]
+            shared_r.add(name_of(es))
+        elif template == "ratemonitor":
+            shared_r.add(name_of(codeobj.variables["_spikespace"]))
+        if template in ("spikemonitor", "statemonitor", "ratemonitor"):
+            for var in self._monitor_buffers(codeobj):
+                shared_w.add(name_of(var))
+        # scalars that never change inside a run cannot create a dependency
+        drop = set()
+        for var in codeobj.variables.values():
+            if isinstance(var, ArrayVariable) and clock_field(var) is not None:
+                drop.add(name_of(var))
+        return priv_r - drop, priv_w - drop, shared_r - drop, shared_w - drop
+
+    def _plan_barriers(self, entries):
+        """Greedy phase construction: a grid barrier is placed in front of a code object iff it
+        conflicts (RAW/WAR/WAW on an array, unless both accesses are element-private with the
+        same owned partition) with something executed since the previous barrier."""
+        items = []
+        ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
+        for clock, codeobj in entries:
+            if not self.is_device_codeobj(codeobj):
+                raise NotImplementedError(
+                    f"Code object '{codeobj.name}' cannot run inside the simulation loop on the b200 device"
+                )
+            info = self._b200_info[codeobj.name]
+            if info["template"] == "synapses_push_spikes":
+                continue
+            pr, pw, sr, sw = self._codeobj_access(codeobj)
+            conflict = bool(
+                (sw | pw) & (ph_sr | ph_sw)      # I write what somebody read/wrote (shared)
+                or sw & (ph_pr | ph_pw)           # shared write vs private access
+                or (sr | pr) & ph_sw              # I read what somebody wrote (shared)
+                or sr & ph_pw                     # shared read of a privately written array
+            )
+            if conflict:
+                ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
+            items.append({"name": codeobj.name, "barrier": conflict and len(items) > 0})
+            ph_pr |= pr
+            ph_pw |= pw
+            ph_sr |= sr
+            ph_sw |= sw
+        return items
+
+    # ------------------------------------------------------------------------------------------
+    # monitors
+    # ------------------------------------------------------------------------------------------
+    def _monitor_buffers(self, codeobj):
+        info = self._b200_info[codeobj.name]
+        owner = info["owner"]
+        template = info["template"]
+        if template == "spikemonitor":
+            names = sorted(info["template_kwds"].get("record_variables", {}).keys())
+            return [owner.variables[n] for n in names]
+        if template == "statemonitor":
+            rec = info["template_kwds"].get("_recorded_variables", {})
+            return [owner.variables["t"]] + [rec[k] for k in sorted(rec.keys())]
+        if template == "ratemonitor":
+            return [owner.variables["rate"], owner.variables["t"]]
+        return []
+
+    def _collect_monitors(self):
+        monitors = []
+        for codeobj in self.code_objects.values():
+            if not self.is_device_codeobj(codeobj):
+                continue
+            info = self._b200_info[codeobj.name]
+            template = info["template"]
+            if template not in ("spikemonitor", "statemonitor", "ratemonitor"):
+                continue
+            owner = info["owner"]
+            kind = {"spikemonitor": "spike", "statemonitor": "state", "ratemonitor": "rate"}[template]
+            buffers = []
+            width = 1
+            if template == "statemonitor":
+                width = int(owner.variables["_indices"].size)
+            for var in self._monitor_buffers(codeobj):
+                ndim = getattr(var, "ndim", 1)
+                buffers.append(
+                    {
+                        "name": self.arrays[var],
+                        "ctype": c_data_type(var.dtype),
+                        "ndim": ndim,
+                        "width": width if ndim == 2 else 1,
+                    }
+                )
+            headroom = 1
+            if template == "spikemonitor":
+                headroom = max(1, int(owner.source.stop - owner.source.start))
+            monitors.append(
+                {
+                    "name": owner.name,
+                    "kind": kind,
+                    "N_array": self.arrays[owner.variables["N"]],
+                    "buffers": buffers,
+                    "headroom": headroom,
+                    "width": width,
+                }
+            )
+        return monitors
+
+    # ------------------------------------------------------------------------------------------
+    # source generation
+    # ------------------------------------------------------------------------------------------
+    def _array_table(self, monitors):
+        """Description of every array for the device array table template."""
+        used, written = set(), set()
+        for codeobj in self.code_objects.values():
+            if not self.is_device_codeobj(codeobj):
+                continue
+            for var in codeobj.variables.values():
+                if isinstance(var, ArrayVariable):
+                    used.add(var)
+            if self._b200_info[codeobj.name]["template"] == "synapses_push_spikes":
+                continue
+            _, pw, _, sw = self._codeobj_access(codeobj)
+            names = pw | sw
+            for var in codeobj.variables.values():
+                if isinstance(var, ArrayVariable) and self.get_array_name(var, access_data=False) in names:
+                    written.add(var)
+        monitor_of, min_cap = {}, {}
+        for mon in monitors:
+            for b in mon["buffers"]:
+                monitor_of[b["name"]] = mon["name"]
+                min_cap[b["name"]] = max(64 * mon["headroom"], 1 << 16) if mon["kind"] == "spike" else 1024
+        table = []
+        for var, name in sorted(self.arrays.items(), key=lambda kv: kv[1]):
+            try:
+                owner_name = var.owner.name
+            except (ReferenceError, AttributeError):
+                owner_name = "_unknown"
+            entry = {
+                "name": name,
+                "ctype": c_data_type(var.dtype),
+                "used": var in used,
+                "written": var in written,
+                "user_name": f"{owner_name}.{var.name}",
+                "monitor": monitor_of.get(name),
+                "min_cap": min_cap.get(name, 0),
+                "eventspace": False,
+                "clock": None,
+                "width": 1,
+                "dyn_name": None,
+                "size": 0,
+            }
+            if var in self.dynamic_arrays:
+                entry["kind"] = "dynamic1d"
+                entry["dyn_name"] = self.dynamic_arrays[var]
+            elif var in self.dynamic_arrays_2d:
+                entry["kind"] = "dynamic2d"
+                entry["dyn_name"] = self.dynamic_arrays_2d[var]
+                width = 1
+                for mon in monitors:
+                    if mon["name"] == monitor_of.get(name):
+                        width = mon["width"]
+                entry["width"] = width
+            else:
+                entry["kind"] = "static"
+                entry["size"] = int(var.size)
+                if is_eventspace(var):
+                    entry["eventspace"] = True
+                    entry["clock"] = var.owner.clock.name
+                if clock_field(var) is not None:
+                    entry["used"] = False   # clocks travel by value
+            table.append(entry)
+        return table
+
+    def _eventspaces(self):
+        spaces = {}
+        for codeobj in self.code_objects.values():
+            if not self.is_device_codeobj(codeobj):
+                continue
+            for var in codeobj.variables.values():
+                if is_eventspace(var):
+                    spaces[self.arrays[var]] = {
+                        "name": self.arrays[var],
+                        "size": int(var.size),
+                        "clock": var.owner.clock.name,
+                    }
+        return [spaces[k] for k in sorted(spaces)]
+
+    def _pathways(self, synapses):
+        out = []
+        for S in sorted(synapses, key=lambda s: s.name):
+            for path in sorted(S._pathways, key=lambda p: p.name):
+                out.append(
+                    {
+                        "name": path.name,
+                        "sources": self.dynamic_arrays[path.synapse_sources],
+                        "start": int(path.source.start),
+                        "stop": int(path.source.stop),
+                    }
+                )
+        return out
+
+    def generate_objects_source(
+        self, writer, arange_arrays, synapses, static_array_specs, networks, timed_arrays
+    ):
+        # host mirrors: the reference's own objects.cpp, minus its SynapticPathway objects
+        host_tmp = CPPStandaloneCodeObject.templater.objects(
+            None,
+            None,
+            array_specs=self.arrays,
+            dynamic_array_specs=self.dynamic_arrays,
+            dynamic_array_2d_specs=self.dynamic_arrays_2d,
+            zero_arrays=self.zero_arrays,
+            arange_arrays=arange_arrays,
+            synapses=[],
+            clocks=self.clocks,
+            static_array_specs=static_array_specs,
+            networks=networks,
+            get_array_filename=self.get_array_filename,
+            get_array_name=self.get_array_name,
+            profiled_codeobjects=[],
+            code_objects=list(self.code_objects.values()),
+            timed_arrays=timed_arrays,
+        )
+        writer.write("objects.*", host_tmp)
+        monitors = self._collect_monitors()
+        dev_tmp = B200CodeObject.templater.b200_objects(
+            None,
+            None,
+            clocks=self.clocks,
+            array_specs=self.arrays,
+            b200_arrays=self._array_table(monitors),
+            b200_eventspaces=self._eventspaces(),
+            b200_pathways=self._pathways(synapses),
+            b200_monitors=monitors,
+        )
+        writer.write("b200_objects.h", dev_tmp.h_file)
+        writer.write("b200_objects.cpp", dev_tmp.cpp_file)
+
+    def generate_main_source(self, writer):
+        # reuse the inherited construction of `main_lines`; the template lookup goes through
+        # code_object_class() and therefore renders OUR main template
+        B200CodeObject.templater.env.globals["profiled_codeobjects"] = list(self.profiled_codeobjects)
+        super().generate_main_source(writer)
+
+    def generate_run_source(self, writer):
+        run_tmp = CPPStandaloneCodeObject.templater.run(
+            None,
+            None,
+            run_funcs=self.runfuncs,
+            code_objects=list(self.code_objects.values()),
+            user_headers=self.headers,
+            array_specs=self.arrays,
+            clocks=self.clocks,
+        )
+        writer.write("run.*", run_tmp)
+
+    def _constant_lines(self, codeobj, device_side):
+        """The `%CONSTANTS%` block of one code object (cf. device.py:908-940): array sizes and
+        namespace constants; on the device side dynamic-array sizes come from the table `_A`."""
+        renderer = CPPNodeRenderer()
+        lines = []
+        for k, v in codeobj.variables.items():
+            if isinstance(v, ArrayVariable):
+                try:
+                    if isinstance(v, DynamicArrayVariable):
+                        if v.ndim == 1:
+                            arr, dyn = self.arrays[v], self.dynamic_arrays[v]
+                            ctype = c_data_type(v.dtype)
+                            if device_side:
+                                lines.append(f"const size_t _num{k} = _A._n{arr};")
+                            else:
+                                lines.append(f"{ctype}* const {arr} = {dyn}.empty()? 0 : &{dyn}[0];")
+                                lines.append(f"const size_t _num{k} = {dyn}.size();")
+                    else:
+                        lines.append(f"const size_t _num{k} = {v.size};")
+                except TypeError:
+                    pass
+            elif isinstance(v, Constant):
+                value = renderer.render_expr(repr(v.value))
+                lines.append(f"const {c_data_type(v.dtype)} {k} = {value};")
+        seen, unique = set(), []
+        for line in lines:
+            if line not in seen:
+                seen.add(line)
+                unique.append(line)
+        return "\n".join(unique)
+
+    def generate_codeobj_source(self, writer):
+        device_objs = []
+        for codeobj in self.code_objects.values():
+            host_consts = self._constant_lines(codeobj, device_side=False)
+            for block in codeobj.before_after_blocks:
+                cpp_code = getattr(codeobj.code, f"{block}_cpp_file").replace("%CONSTANTS%", host_consts)
+                writer.write(f"code_objects/{block}_{codeobj.name}.cpp", cpp_code)
+                writer.write(f"code_objects/{block}_{codeobj.name}.h", getattr(codeobj.code, f"{block}_h_file"))
+            if self.is_device_codeobj(codeobj):
+                dev_consts = self._constant_lines(codeobj, device_side=True)
+                code = codeobj.code.cpp_file.replace("%CONSTANTS_DEV%", dev_consts)
+                code = code.replace("%CONSTANTS%", host_consts)
+                writer.write(f"code_objects/{codeobj.name}.cuh", code)
+                device_objs.append(codeobj)
+            else:
+                code = codeobj.code.cpp_file.replace("%CONSTANTS%", host_consts)
+                writer.write(f"code_objects/{codeobj.name}.cpp", code)
+            writer.write(f"code_objects/{codeobj.name}.h", codeobj.code.h_file)
+
+        # persistent kernels: one per run() call
+        plans = []
+        for index, entries in enumerate(self._b200_plans):
+            clocks = {clock for clock, _ in entries}
+            plan = {"index": index, "entries": [], "clock": None, "signature": "", "n_barriers": 0}
+            if len(clocks) == 1 and prefs.devices.b200.persistent and not self.enable_profiling_any:
+                clock = next(iter(clocks))
+                try:
+                    items = self._plan_barriers(entries)
+                    plan["entries"] = items
+                    plan["clock"] = clock.name
+                    plan["signature"] = " ".join(
+                        ("| " if it["barrier"] else "") + it["name"] for it in items
+                    )
+                    plan["n_barriers"] = 1 + sum(1 for it in items if it["barrier"])
+                except NotImplementedError as ex:
+                    logger.warn(f"run #{index} falls back to stepwise execution: {ex}")
+            plans.append(plan)
+        self._b200_plan_info = plans
+        user_headers = self.headers + prefs["codegen.cpp.headers"]
+        kernels = B200CodeObject.templater.b200_kernels(
+            None,
+            None,
+            device_code_objects=device_objs,
+            plans=[p for p in plans],
+            user_headers=user_headers,
+            profiled=bool(self.enable_profiling_any),
+            ctas_per_sm=int(prefs.devices.b200.ctas_per_sm),
+        )
+        writer.write("b200_kernels.cu", kernels)
+        self.cu_source_files = ["b200_kernels.cu"]
+        writer.write("b200_plans.h", B200CodeObject.templater.b200_plans(None, None, plans=plans))
+
+    @property
+    def enable_profiling_any(self):
+        return bool(self.profiled_codeobjects)
+
+    def copy_source_files(self, writer, directory):
+        super().copy_source_files(writer, directory)
+        # the spike queue of the reference is not compiled into a b200 project
+        writer.source_files.discard("brianlib/spikequeue.cpp")
+        writer.header_files.discard("brianlib/spikequeue.h")
+        clocks = B200CodeObject.templater.b200_clocks(None, None)
+        with open(os.path.join(directory, "brianlib", "clocks.h"), "w") as f:
+            f.write(clocks)
+        for fname in sorted(os.listdir(CSRC_DIR)):
+            if fname.endswith((".h", ".cuh")):
+                shutil.copy2(os.path.join(CSRC_DIR, fname), os.path.join(directory, fname))
+                writer.header_files.add(fname)
+        shutil.copy2(os.path.join(INCLUDE_DIR, "brian2_b200.h"), os.path.join(directory, "brian2_b200.h"))
+        writer.header_files.add("brian2_b200.h")
+
+    @property
+    def library_name(self):
+        return "libb200_project.so"
+
+    def nvcc_flags(self):
+        flags = [prefs.devices.b200.arch_flags] + list(prefs.devices.b200.extra_nvcc_flags)
+        flags.append("-fmad=true" if prefs.devices.b200.fmad else "-fmad=false")
+        if prefs.core.default_float_dtype == np.float32:
+            flags.append("-DB200_FLOAT32")
+        return " ".join(flags)
+
+    def generate_makefile(self, writer, compiler, compiler_flags, linker_flags, nb_threads, debug):
+        if nb_threads:
+            raise NotImplementedError("The b200 device does not use OpenMP threads")
+        sources = sorted(f for f in writer.source_files if f != "brianlib/spikequeue.cpp")
+        makefile = B200CodeObject.templater.makefile(
+            None,
+            None,
+            library_name=self.library_name,
+            source_files=" ".join(sources),
+            cu_source_files=" ".join(self.cu_source_files),
+            header_files=" ".join(sorted(writer.header_files)),
+            compiler_flags=compiler_flags,
+            compiler_debug_flags="-g -DDEBUG" if debug else "",
+            linker_debug_flags="-g" if debug else "",
+            linker_flags=linker_flags,
+            nvcc=prefs.devices.b200.nvcc,
+            cuda_home=prefs.devices.b200.cuda_home,
+            nvcc_flags=self.nvcc_flags(),
+            nvcc_arch=prefs.devices.b200.arch_flags,
+            rm_cmd="rm -f $(OBJS) $(CU_OBJS) $(LIBRARY)",
+        )
+        writer.write("makefile", makefile)
+
+    # ------------------------------------------------------------------------------------------
+    # running: in-process through the C ABI
+    # ------------------------------------------------------------------------------------------
+    def _run_library(self, cmd, stdout):
+        """Replacement of ``subprocess.call(['./main', ...])``: load a fresh copy of the project
+        library and call ``b200_run_main`` with the same arguments."""
+        args = list(cmd[1:])   # cmd[0] is the reference's "./main"
+        lib_path = os.path.join(os.getcwd(), self.library_name)
+        self._b200_run_counter += 1
+        lib = B200Library(lib_path, fresh_copy=self._b200_run_counter > 1)
+        lib.set_option("mode", 0 if prefs.devices.b200.persistent else 1)
+        lib.set_option("max_chunk", int(prefs.devices.b200.max_chunk))
+        lib.set_option("ctas_per_sm", int(prefs.devices.b200.ctas_per_sm))
+        lib.set_option("grid", int(prefs.devices.b200.grid))
+        self._b200_library = lib
+        status = lib.run_main(args, stdout=stdout)
+        if status != 0:
+            sys.stderr.write(f"b200 run failed: {lib.last_error()}\n")
+        return status
+
+    def run(self, directory=None, results_directory=None, with_output=True, run_args=None):
+        import brian2.devices.cpp_standalone.device as _ref_device_module
+
+        original = _ref_device_module.subprocess
+        _ref_device_module.subprocess = _SubprocessShim(self._run_library)
+        try:
+            super().run(
+                directory=directory,
+                results_directory=results_directory,
+                with_output=with_output,
+                run_args=run_args,
+            )
+        finally:
+            _ref_device_module.subprocess = original
+
+    # counters of the last run (for benchmarks)
+    def counter(self, key):
+        if self._b200_library is None:
+            raise RuntimeError("The b200 project has not been run yet")
+        return self._b200_library.get_counter(key)
+
+
+b200_device = B200Device()
+all_devices["b200"] = b200_device

@@ -1,0 +1,144 @@
+{# The single CUDA translation unit of a b200 project: the __constant__ array table, every
+   in-loop code object as a __device__ function (+ its own kernel for stepwise mode) and one
+   persistent cooperative step kernel per run() call. #}
+#include "b200_objects.h"
+#include "b200_runtime.cuh"
+#include "b200_functions.cuh"
+#include "network.h"
+#include "b200_plans.h"
+#include <cooperative_groups.h>
+#include <chrono>
+#include <map>
+#include <string>
+#include <cmath>
+#include <climits>
+{% for name in user_headers | sort %}
+#include {{name}}
+{% endfor %}
+
+__constant__ _B200Arrays _A;
+
+void _b200_sync_constants()
+{
+    B200_CUDA(cudaMemcpyToSymbol(_A, &_A_host, sizeof(_B200Arrays)));
+}
+
+// ---- launch bookkeeping (kernel count for the bench contract, optional per-object timing) ----
+static std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t> > _b200_prof_events;
+std::map<std::string, double> _b200_prof_seconds;
+bool _b200_profiling = {{ 'true' if profiled else 'false' }};
+int _b200_ctas_per_sm = {{ctas_per_sm}};
+int _b200_grid_override = 0;
+
+void _b200_launch_begin(const char* name)
+{
+    b200::state().launches++;
+    if (_b200_profiling) {
+        std::pair<cudaEvent_t, cudaEvent_t>& ev = _b200_prof_events[name];
+        if (!ev.first) { B200_CUDA(cudaEventCreate(&ev.first)); B200_CUDA(cudaEventCreate(&ev.second)); }
+        B200_CUDA(cudaEventRecord(ev.first, b200::state().stream));
+    }
+}
+void _b200_launch_end(const char* name)
+{
+    B200_CUDA(cudaGetLastError());
+    if (_b200_profiling) {
+        std::pair<cudaEvent_t, cudaEvent_t>& ev = _b200_prof_events[name];
+        B200_CUDA(cudaEventRecord(ev.second, b200::state().stream));
+        B200_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        _b200_prof_seconds[name] += 1e-3 * ms;
+    }
+}
+
+// co-resident grid for a kernel: the thresholder's look-back and the grid barrier both need
+// every CTA to be resident, and the look-back polls with one thread per predecessor CTA
+static int _b200_grid_for(const void* kernel)
+{
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, b200::kBlock, 0));
+    if (occ < 1) throw std::runtime_error("b200: kernel cannot be resident (registers/shared memory)");
+    int grid = std::min(occ, _b200_ctas_per_sm) * b200::state().num_sms;
+    if (_b200_grid_override > 0) grid = std::min(grid, _b200_grid_override);
+    return std::max(1, std::min(grid, b200::kBlock));
+}
+#define B200_GRID(kernel) ([]() { static int g = 0; static int ov = -1; \
+    if (!g || ov != _b200_grid_override) { ov = _b200_grid_override; g = _b200_grid_for((const void*)kernel); } return g; }())
+
+{% for codeobj in device_code_objects %}
+#include "code_objects/{{codeobj.name}}.cuh"
+{% endfor %}
+
+{% for plan in plans %}
+{% if plan.clock %}
+// =============================================================================================
+// persistent step kernel for run() call #{{plan.index}}
+//   schedule: {{plan.signature}}
+//   grid barriers per step: {{plan.n_barriers}} (incl. the end-of-step barrier)
+// =============================================================================================
+struct _B200Scal_{{plan.index}} {
+    {% for item in plan.entries %}
+    _co_{{item.name}}::Scal {{item.name}};
+    {% endfor %}
+    int _unused;
+};
+
+__global__ void __launch_bounds__(b200::kBlock)
+_b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
+{
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x};
+    unsigned long long _bar_target = 0ULL;
+    __shared__ int _s_stop;
+    _B200Clocks _clks = _clks0;
+    long long _step = 0;
+    while (_step < _nsteps)
+    {
+        if (_ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
+            _A._ctrl->stop = 1;
+        {% for item in plan.entries %}
+        {% if item.barrier %}
+        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx.nb);
+        {% endif %}
+        _dev_{{item.name}}(_ctx, _clks, _sc.{{item.name}});
+        {% endfor %}
+        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx.nb);
+        if (threadIdx.x == 0) _s_stop = b200::ld_volatile_s32(&_A._ctrl->stop);
+        __syncthreads();
+        const int _stop = _s_stop;
+        // Clock::tick (brianlib/clocks.h:34-38)
+        _clks.{{plan.clock}}.timestep += 1;
+        _clks.{{plan.clock}}.t = _clks.{{plan.clock}}.timestep * _clks.{{plan.clock}}.dt;
+        ++_step;
+        if (_stop) break;
+        __syncthreads();
+    }
+    if (_ctx.bid == 0 && threadIdx.x == 0) _A._ctrl->steps_done = (int)_step;
+}
+
+static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
+{
+    b200::RuntimeState& st = b200::state();
+    _B200Scal_{{plan.index}} sc;
+    {% for item in plan.entries %}
+    _hostscal_{{item.name}}(sc.{{item.name}});
+    {% endfor %}
+    sc._unused = 0;
+    if (nsteps > INT_MAX) nsteps = INT_MAX;
+    B200_CUDA(cudaMemsetAsync(st.control, 0, sizeof(b200::Control), st.stream));
+    _B200Clocks clks = _b200_clocks_now();
+    void* args[] = {(void*)&clks, (void*)&nsteps, (void*)&sc};
+    const int grid = B200_GRID(_b200_persistent_{{plan.index}});
+    _b200_launch_begin("persistent_{{plan.index}}");
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)_b200_persistent_{{plan.index}}, dim3(grid), dim3(b200::kBlock), args, 0, st.stream));
+    _b200_launch_end("persistent_{{plan.index}}");
+    B200_CUDA(cudaMemcpyAsync(st.control_host, st.control, sizeof(b200::Control), cudaMemcpyDeviceToHost, st.stream));
+    B200_CUDA(cudaStreamSynchronize(st.stream));
+    return (long long)st.control_host->steps_done;
+}
+const B200Plan _b200_plan_{{plan.index}} = { _b200_run_chunk_{{plan.index}}, "{{plan.signature}}" };
+{% else %}
+// run() call #{{plan.index}}: stepwise execution (several clocks, profiling, or persistent mode off)
+const B200Plan _b200_plan_{{plan.index}} = { 0, "stepwise" };
+{% endif %}
+{% endfor %}

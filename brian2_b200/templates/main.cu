@@ -1,0 +1,156 @@
+{# Entry points of a b200 project.  The reference emits `int main()` and is run as a subprocess
+   (templates/main.cpp:47-75, device.py:1311); here the same sequence of main_lines is exposed
+   through the C ABI declared in include/brian2_b200.h and called in-process via ctypes. #}
+#include <stdlib.h>
+#include "objects.h"
+#include "b200_objects.h"
+#include "b200_plans.h"
+#include <csignal>
+#include <ctime>
+#include <time.h>
+#include "run.h"
+#include "brianlib/common_math.h"
+#include "brian2_b200.h"
+
+{% for codeobj in code_objects | sort(attribute='name') %}
+#include "code_objects/{{codeobj.name}}.h"
+{% for block in codeobj.before_after_blocks %}
+#include "code_objects/{{block}}_{{codeobj.name}}.h"
+{% endfor %}
+{% endfor %}
+
+{% for name in user_headers | sort %}
+#include {{name}}
+{% endfor %}
+
+#include <iostream>
+#include <fstream>
+#include <string>
+#include <map>
+
+{{report_func|autoindent}}
+
+extern std::map<std::string, double> _b200_prof_seconds;
+extern bool _b200_profiling;
+extern int _b200_ctas_per_sm;
+extern int _b200_grid_override;
+
+static std::string _b200_error;
+
+void set_from_command_line(const std::vector<std::string> args)
+{
+    for (const auto& arg : args) {
+        size_t equal_sign = arg.find("=");
+        auto name = arg.substr(0, equal_sign);
+        auto value = arg.substr(equal_sign + 1, arg.length());
+        brian::set_variable_by_name(name, value);
+    }
+}
+
+static void _b200_main(std::vector<std::string> args)
+{
+    std::random_device _rd;
+    if (args.size() >= 2 && args[0] == "--results_dir")
+    {
+        brian::results_dir = args[1];
+        args.erase(args.begin(), args.begin()+2);
+    }
+    {{'\n'.join(code_lines['before_start'])|autoindent}}
+    brian_start();
+    {{'\n'.join(code_lines['after_start'])|autoindent}}
+    {
+        using namespace brian;
+        {{main_lines|autoindent}}
+    }
+    {{'\n'.join(code_lines['before_end'])|autoindent}}
+    _b200_write_profiling();
+    _write_arrays();
+    {{'\n'.join(code_lines['after_end'])|autoindent}}
+}
+
+void _b200_write_profiling()
+{
+    if (!_b200_profiling) return;
+    std::ofstream f(brian::results_dir + "profiling_info.txt");
+    {% for codeobj in profiled_codeobjects | sort %}
+    f << "{{codeobj}}\t" << _b200_prof_seconds["{{codeobj}}"] << std::endl;
+    {% endfor %}
+}
+
+extern "C" {
+
+int b200_run_main(int argc, const char** argv)
+{
+    try {
+        _b200_error.clear();
+        std::vector<std::string> args;
+        for (int i = 0; i < argc; i++) args.push_back(argv[i]);
+        _b200_main(args);
+        return 0;
+    } catch (const std::exception& e) {
+        _b200_error = e.what();
+        return 1;
+    } catch (...) {
+        _b200_error = "unknown C++ exception";
+        return 1;
+    }
+}
+
+const char* b200_last_error() { return _b200_error.c_str(); }
+double b200_last_run_time() { return Network::_last_run_time; }
+double b200_last_run_completed_fraction() { return Network::_last_run_completed_fraction; }
+void b200_request_stop() { if (b200::state().stop_request) *b200::state().stop_request = 1; Network::_globally_stopped = true; }
+
+int b200_set_option(const char* key, double value)
+{
+    const std::string k(key);
+    if (k == "mode") Network::_b200_mode = (int)value;
+    else if (k == "max_chunk") Network::_b200_max_chunk = (long long)value;
+    else if (k == "profile") _b200_profiling = value != 0;
+    else if (k == "ctas_per_sm") _b200_ctas_per_sm = (int)value;
+    else if (k == "grid") _b200_grid_override = (int)value;
+    else if (k == "seed") { b200::state().seed = (unsigned long long)value; b200::state().seeded = true; }
+    else return 1;
+    return 0;
+}
+
+double b200_get_counter(const char* key)
+{
+    const std::string k(key);
+    b200::RuntimeState& st = b200::state();
+    if (k == "launches") return (double)st.launches;
+    if (k == "events") return (double)_b200_events_delivered();
+    if (k == "steps") return (double)Network::_b200_steps_run;
+    if (k == "h2d_bytes") return (double)st.h2d_bytes;
+    if (k == "d2h_bytes") return (double)st.d2h_bytes;
+    if (k == "upload_seconds") return st.upload_seconds;
+    if (k == "download_seconds") return st.download_seconds;
+    if (k == "device_bytes") return (double)st.bytes_allocated;
+    if (k == "num_sms") return (double)st.num_sms;
+    return -1.0;
+}
+
+int b200_profiling(const char** names, double* seconds, int cap)
+{
+    int n = 0;
+    for (std::map<std::string, double>::iterator it = _b200_prof_seconds.begin(); it != _b200_prof_seconds.end() && n < cap; ++it, ++n) {
+        names[n] = it->first.c_str();
+        seconds[n] = it->second;
+    }
+    return n;
+}
+
+long long b200_get_array_size(const char* name) { return _b200_array_nbytes(name); }
+int b200_get_array(const char* name, void* out, size_t nbytes) { return _b200_array_copy_out(name, out, nbytes); }
+int b200_set_array(const char* name, const void* data, size_t nbytes) { return _b200_array_copy_in(name, data, nbytes); }
+
+int b200_finalize()
+{
+    try {
+        _dealloc_arrays();
+        cudaDeviceSynchronize();
+        return 0;
+    } catch (...) { return 1; }
+}
+
+}  // extern "C"

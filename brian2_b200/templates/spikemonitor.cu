@@ -1,0 +1,51 @@
+{# USES_VARIABLES { N, _clock_t, count, _source_start, _source_stop} #}
+{# WRITES_TO_READ_ONLY_VARIABLES { N, count } #}
+{# Spike/event monitor: brian2/devices/cpp_standalone/templates/spikemonitor.cpp:6-51.
+   The recorded ids are a contiguous run of the (ascending) spike list, so every spike's output
+   position is known without atomics: base + (j - first).  The running total N is double
+   buffered by step parity so that all CTAs can read it while one thread publishes the new
+   value.  Storage is a device append buffer; the host grows it between launches when the
+   kernel reports that fewer than one step's worst case of free slots are left. #}
+{% extends 'common_group.cu' %}
+{% block maincode %}
+    {% set _eventspace = get_array_name(eventspace_variable) %}
+    const int32_t* _events = {{_eventspace}};
+    const int _num_events_all = _events[_num{{eventspace_variable.name}} - 1];
+    const int _start_idx = b200::lower_bound_i32(_events, _num_events_all, (int)_source_start);
+    const int _end_idx = b200::lower_bound_i32(_events, _num_events_all, (int)_source_stop);
+    const int _num_events = _end_idx - _start_idx;
+    const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
+    long long* _monN = _A._monN_{{owner.name}};
+    const long long _N_old = _monN[_par];
+    if (_num_events > 0)
+    {
+        const int _vectorisation_idx = 1;
+        {{scalar_code|autoindent}}
+        for (int _j = _start_idx + _ctx.bid * b200::kBlock + threadIdx.x; _j < _end_idx;
+             _j += _ctx.nb * b200::kBlock)
+        {
+            const int _idx = _events[_j];
+            const int _vectorisation_idx = _idx;
+            {{vector_code|autoindent}}
+            const long long _out = _N_old + (_j - _start_idx);
+            {% for varname, var in record_variables | dictsort %}
+            _A.{{b200_field(var)}}[_out] = _to_record_{{varname}};
+            {% endfor %}
+            {{count}}[_idx - _source_start]++;
+        }
+    }
+    if (_ctx.bid == 0 && threadIdx.x == 0)
+    {
+        const long long _N_new = _N_old + _num_events;
+        _monN[1 - _par] = _N_new;
+        {{N}} = (int32_t)_N_new;
+        {% if record_variables %}
+        {% set _first = (record_variables | dictsort | first)[1] %}
+        if (_N_new + (long long)(_source_stop - _source_start) > (long long)_A._cap{{b200_field(_first)}})
+        {
+            _A._ctrl->overflow = 1;
+            _A._ctrl->stop = 1;
+        }
+        {% endif %}
+    }
+{% endblock %}

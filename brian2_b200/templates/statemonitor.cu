@@ -1,0 +1,29 @@
+{# USES_VARIABLES { t, _clock_t, _indices, N } #}
+{# WRITES_TO_READ_ONLY_VARIABLES { t, N } #}
+{# State monitor: brian2/devices/cpp_standalone/templates/statemonitor.cpp:5-42.  One row of
+   the row-major (steps x n_rec) device buffer per call; the host sizes the buffer for the
+   whole launch beforehand, so there is no resize in the loop. #}
+{% extends 'common_group.cu' %}
+{% block maincode %}
+    const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
+    long long* _monN = _A._monN_{{owner.name}};
+    const long long _row = _monN[_par];
+    if (_ctx.bid == 0 && threadIdx.x == 0)
+    {
+        _A.{{b200_field(variables['t'])}}[_row] = {{_clock_t}};
+        _monN[1 - _par] = _row + 1;
+        {{N}} = (int32_t)(_row + 1);
+    }
+    // scalar code
+    {{scalar_code|autoindent}}
+    for (int _i = _ctx.bid * b200::kBlock + threadIdx.x; _i < (int)_num_indices;
+         _i += _ctx.nb * b200::kBlock)
+    {
+        const int _idx = {{_indices}}[_i];
+        const int _vectorisation_idx = _idx;
+        {{vector_code|autoindent}}
+        {% for varname, var in _recorded_variables | dictsort %}
+        _A.{{b200_field(var)}}[_row * (long long)_num_indices + _i] = _to_record_{{varname}};
+        {% endfor %}
+    }
+{% endblock %}

@@ -1,0 +1,87 @@
+/* brian2_b200.h -- C ABI of a built `b200` project (the shared library that replaces the
+ * `./main` executable of Brian2's cpp_standalone device).
+ *
+ * Every generated project exports exactly these symbols; Python binds them with ctypes
+ * (brian2_b200/capi.py).  Plain pointers and sizes only -- no C++ / torch types.
+ *
+ * Reference interfaces replaced (brian-team/brian2, paths relative to brian2/):
+ *   b200_run_main ................ `int main(argc, argv)` of the generated project,
+ *                                   devices/cpp_standalone/templates/main.cpp:47-75, started with
+ *                                   subprocess.call(["./main", "--results_dir", dir] + run_args),
+ *                                   devices/cpp_standalone/device.py:1311.  Arguments have the same
+ *                                   meaning ("--results_dir <dir>", then "group.var=value|file").
+ *   b200_last_run_time /
+ *   b200_last_run_completed_fraction  results/last_run_info.txt, templates/objects.cpp:364-374,
+ *                                   read back at device.py:1326-1332 (Network::_last_run_time,
+ *                                   templates/network.cpp:14-15,114-118).
+ *   b200_get_array(_size) ........ results/<array>_<crc32> raw dumps, templates/objects.cpp:270-323,
+ *                                   read by CPPStandaloneDevice.get_value, device.py:544-580.
+ *   b200_set_array ............... static_arrays/<name> + `name=file` run arguments,
+ *                                   templates/objects.cpp:91-150 (set_variable_by_name), device.py:1114.
+ *   b200_profiling ............... results/profiling_info.txt, templates/objects.cpp:349-363,
+ *                                   device.py:1991-2002.
+ *   b200_request_stop ............ SIGINT handler / Network::_globally_stopped,
+ *                                   templates/main.cpp:38-51, templates/network.cpp:16-17,65-67.
+ *   b200_last_error .............. non-zero exit status + stderr of ./main, device.py:1316-1324.
+ *   b200_set_option / b200_get_counter   no reference counterpart (device preferences and the
+ *                                   counters bench.py reports: kernel launches, synaptic events,
+ *                                   host<->device bytes).
+ *
+ * Conventions: functions returning int return 0 on success, non-zero on failure with the
+ * message available from b200_last_error().  The library never calls exit().  Buffers passed in
+ * or out are owned by the caller (copy semantics).  Not re-entrant: one run at a time.
+ */
+#ifndef BRIAN2_B200_H
+#define BRIAN2_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Run the whole generated main(): host-side initialisation code objects (reference C++,
+ * bit-identical RNG stream), upload, the device time loop(s), download, result files. */
+int b200_run_main(int argc, const char** argv);
+
+/* Message of the last failure ("" if none).  Valid until the next call. */
+const char* b200_last_error(void);
+
+/* Wall-clock seconds of the last Network::run time loop (uploads/downloads excluded, exactly
+ * like the reference excludes file I/O) and the completed fraction of its duration. */
+double b200_last_run_time(void);
+double b200_last_run_completed_fraction(void);
+
+/* Ask a running simulation to stop after the current step (callable from another thread). */
+void b200_request_stop(void);
+
+/* Options, to be set before b200_run_main:
+ *   "mode"        0 = persistent step kernel when possible (default), 1 = one launch per code object
+ *   "max_chunk"   steps per persistent launch
+ *   "profile"     1 = per-code-object CUDA-event timing (forces mode 1 semantics per launch)
+ *   "ctas_per_sm" resident CTAs per SM used to size grids
+ *   "grid"        upper bound on the number of CTAs (0 = none)
+ *   "seed"        seed of the device RNG streams */
+int b200_set_option(const char* key, double value);
+
+/* Counters: "launches", "events" (delivered synaptic events), "steps", "h2d_bytes",
+ * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms".  -1 if unknown. */
+double b200_get_counter(const char* key);
+
+/* Per-code-object device seconds (profile mode).  Fills up to `cap` entries, returns the count.
+ * The name pointers stay valid until b200_finalize. */
+int b200_profiling(const char** names, double* seconds, int cap);
+
+/* Host mirrors by name: either the array name ("_array_neurongroup_v",
+ * "_dynamic_array_spikemonitor_t") or "owner.variable" ("neurongroup.v").
+ * b200_get_array_size returns the size in bytes or -1. */
+long long b200_get_array_size(const char* name);
+int b200_get_array(const char* name, void* out, size_t nbytes);
+int b200_set_array(const char* name, const void* data, size_t nbytes);
+
+/* Free host mirrors and device memory. */
+int b200_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIAN2_B200_H */

@@ -1,0 +1,54 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(brian-team/brian2, `cpp_standalone` device, serial, strict floating-point flags -- SURVEY.md
+section 8c) on the model scripts of tests/models.py.
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference):
+    python tests/golden/make_golden.py [case ...]
+The resulting .npz files are committed; the GPU box never needs the reference to check parity.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from brian2_b200._brian2_path import ensure_brian2_importable  # noqa: E402
+
+ensure_brian2_importable()
+import brian2 as b  # noqa: E402
+
+import models  # noqa: E402
+
+#: case name -> (model, kwargs).  Sizes are chosen so that every fixture stays small.
+CASES = {
+    "cuba_4000": ("cuba", dict(N=4000, p=0.02, duration=0.2)),
+    "cuba_1000": ("cuba", dict(N=1000, p=0.08, duration=0.1)),
+    "cobahh_1000": ("cobahh", dict(N=1000, duration=0.05)),
+    "brunel_hetero": ("brunel", dict(N_E=800, epsilon=0.1, duration=0.1, hetero_delays=True)),
+    "brunel_homog": ("brunel", dict(N_E=800, epsilon=0.1, duration=0.1, hetero_delays=False)),
+    "stdp_1000": ("stdp", dict(N=1000, duration=0.2)),
+    "synapses_only": ("synapses_only", dict(N=2000, p=0.2, rate_hz=100.0, duration=0.005)),
+    "synapses_only_delay": ("synapses_only", dict(N=2000, p=0.2, rate_hz=100.0, duration=0.005, delay_steps=3)),
+}
+
+
+def main(argv):
+    names = argv or list(CASES)
+    for case in names:
+        model, kwds = CASES[case]
+        d = tempfile.mkdtemp(prefix=f"golden_{case}_")
+        objs, res = models.run_model(b, model, "cpp_standalone", d, **kwds)
+        res = {k: v for k, v in res.items() if k != "last_run_time"}
+        path = os.path.join(HERE, f"{case}.npz")
+        np.savez_compressed(path, **res)
+        summary = {k: (v.shape, str(v.dtype)) for k, v in res.items()}
+        print(case, os.path.getsize(path), "bytes", summary)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

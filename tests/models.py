@@ -1,0 +1,249 @@
+"""Brian2 model scripts shared by the golden-vector generator (reference ``cpp_standalone``), the
+parity tests (``b200`` device) and ``bench.py``.  Every builder takes the already-imported
+``brian2`` namespace module ``b`` and returns a dict of the objects whose state is compared.
+
+Sources of the models (reference repository): ``examples/CUBA.py``, ``examples/COBAHH.py``,
+``examples/frompapers/Brunel_2000.py``, ``examples/synapses/STDP.py``,
+``brian2/tests/features/speed.py:263-326`` (SynapsesOnly stress).
+"""
+import numpy as np
+
+#: strict floating-point flags for the parity oracle
+STRICT_GCC_FLAGS = ["-w", "-O3", "-std=c++17", "-ffp-contract=off"]
+
+
+def cuba(b, N=4000, p=0.02, duration=0.2, seed=1234, monitor=True):
+    """examples/CUBA.py (4000 LIF, 2 % connectivity, exact integration)."""
+    b.seed(seed)
+    ms, mV = b.ms, b.mV
+    taum = 20 * ms; taue = 5 * ms; taui = 10 * ms  # noqa: E702
+    Vt = -50 * mV; Vr = -60 * mV; El = -49 * mV  # noqa: E702
+    eqs = """
+    dv/dt  = (ge+gi-(v-El))/taum : volt (unless refractory)
+    dge/dt = -ge/taue : volt
+    dgi/dt = -gi/taui : volt
+    """
+    P = b.NeuronGroup(N, eqs, threshold="v>Vt", reset="v = Vr", refractory=5 * ms, method="exact",
+                      namespace=dict(taum=taum, taue=taue, taui=taui, Vt=Vt, Vr=Vr, El=El))
+    P.v = "Vr + rand() * (Vt - Vr)"
+    P.ge = 0 * mV
+    P.gi = 0 * mV
+    we = (60 * 0.27 / 10) * mV
+    wi = (-20 * 4.5 / 10) * mV
+    Ne = int(0.8 * N)
+    Ce = b.Synapses(P, P, on_pre="ge += we", namespace=dict(we=we))
+    Ci = b.Synapses(P, P, on_pre="gi += wi", namespace=dict(wi=wi))
+    Ce.connect(f"i<{Ne}", p=p)
+    Ci.connect(f"i>={Ne}", p=p)
+    objs = dict(P=P, Ce=Ce, Ci=Ci)
+    if monitor:
+        objs["spikes"] = b.SpikeMonitor(P)
+    net = b.Network(*objs.values())
+    objs["net"] = net
+    objs["duration"] = duration
+    objs["state"] = [("P", "v"), ("P", "ge"), ("P", "gi")]
+    return objs
+
+
+def cobahh(b, N=4000, duration=0.1, seed=1234, monitor=True, n_syn_per_neuron=80.0, trace=(1, 10, 100)):
+    """examples/COBAHH.py equations; connectivity p = 80/N as brian2/tests/features/speed.py:198."""
+    b.seed(seed)
+    ms, mV, cm, um, msiemens, uF, siemens, nS = b.ms, b.mV, b.cm, b.um, b.msiemens, b.uF, b.siemens, b.nS
+    area = 20000 * um ** 2
+    ns = dict(
+        Cm=(1 * uF * cm ** -2) * area, gl=(5e-5 * siemens * cm ** -2) * area, El=-60 * mV,
+        EK=-90 * mV, ENa=50 * mV, g_na=(100 * msiemens * cm ** -2) * area,
+        g_kd=(30 * msiemens * cm ** -2) * area, VT=-63 * mV, taue=5 * ms, taui=10 * ms,
+        Ee=0 * mV, Ei=-80 * mV, we=6 * nS, wi=67 * nS,
+    )
+    eqs = b.Equations("""
+    dv/dt = (gl*(El-v)+ge*(Ee-v)+gi*(Ei-v)-
+             g_na*(m*m*m)*h*(v-ENa)-
+             g_kd*(n*n*n*n)*(v-EK))/Cm : volt
+    dm/dt = alpha_m*(1-m)-beta_m*m : 1
+    dn/dt = alpha_n*(1-n)-beta_n*n : 1
+    dh/dt = alpha_h*(1-h)-beta_h*h : 1
+    dge/dt = -ge*(1./taue) : siemens
+    dgi/dt = -gi*(1./taui) : siemens
+    alpha_m = 0.32*(mV**-1)*4*mV/exprel((13*mV-v+VT)/(4*mV))/ms : Hz
+    beta_m = 0.28*(mV**-1)*5*mV/exprel((v-VT-40*mV)/(5*mV))/ms : Hz
+    alpha_h = 0.128*exp((17*mV-v+VT)/(18*mV))/ms : Hz
+    beta_h = 4./(1+exp((40*mV-v+VT)/(5*mV)))/ms : Hz
+    alpha_n = 0.032*(mV**-1)*5*mV/exprel((15*mV-v+VT)/(5*mV))/ms : Hz
+    beta_n = .5*exp((10*mV-v+VT)/(40*mV))/ms : Hz
+    """)
+    P = b.NeuronGroup(N, model=eqs, threshold="v>-20*mV", refractory=3 * ms,
+                      method="exponential_euler", namespace=ns)
+    Ne = int(0.8 * N)
+    Pe = P[:Ne]
+    Pi = P[Ne:]
+    Ce = b.Synapses(Pe, P, on_pre="ge+=we", namespace=ns)
+    Ci = b.Synapses(Pi, P, on_pre="gi+=wi", namespace=ns)
+    Ce.connect(p=n_syn_per_neuron / N)
+    Ci.connect(p=n_syn_per_neuron / N)
+    P.v = "El + (randn() * 5 - 5)*mV"
+    P.ge = "(randn() * 1.5 + 4) * 10.*nS"
+    P.gi = "(randn() * 12 + 20) * 10.*nS"
+    objs = dict(P=P, Ce=Ce, Ci=Ci)
+    if monitor:
+        objs["spikes"] = b.SpikeMonitor(P)
+        if trace:
+            objs["trace"] = b.StateMonitor(P, "v", record=[t for t in trace if t < N])
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("P", "v"), ("P", "ge"), ("P", "gi"), ("P", "m"), ("P", "n"), ("P", "h")]
+    return objs
+
+
+def brunel(b, N_E=800, gamma=0.25, epsilon=0.1, duration=0.1, seed=4321, hetero_delays=True,
+           deterministic=True, monitor=True):
+    """Brunel (2000) sparse E/I LIF network, examples/frompapers/Brunel_2000.py:28-80, with
+    heterogeneous integer delays.  ``deterministic=True`` replaces the Poisson drive by the
+    constant mean drive so that spike trains are comparable bit for bit."""
+    b.seed(seed)
+    ms, mV, Hz = b.ms, b.mV, b.Hz
+    N_I = int(round(gamma * N_E))
+    N = N_E + N_I
+    C_E = int(epsilon * N_E)
+    C_ext = C_E
+    tau = 20 * ms; theta = 20 * mV; V_r = 10 * mV; tau_rp = 2 * ms  # noqa: E702
+    J = 0.1 * mV; D = 1.5 * ms; g = 5.0; nu_ext_over_nu_thr = 2.0  # noqa: E702
+    nu_thr = theta / (J * C_E * tau)
+    nu_ext = nu_ext_over_nu_thr * nu_thr
+    ns = dict(tau=tau, theta=theta, V_r=V_r, J=J, g=g, mu_ext=J * C_ext * nu_ext * tau)
+    if deterministic:
+        eqs = "dv/dt = (-v + mu_ext)/tau : volt (unless refractory)"
+    else:
+        eqs = "dv/dt = -v/tau : volt (unless refractory)"
+    neurons = b.NeuronGroup(N, eqs, threshold="v > theta", reset="v = V_r", refractory=tau_rp,
+                            method="exact", namespace=ns)
+    neurons.v = "rand() * theta"
+    exc = b.Synapses(neurons[:N_E], neurons, on_pre="v += J", namespace=ns)
+    inh = b.Synapses(neurons[N_E:], neurons, on_pre="v += -g*J", namespace=ns)
+    exc.connect(p=epsilon)
+    inh.connect(p=epsilon)
+    if hetero_delays:
+        exc.delay = "(1 + int(rand()*20)) * 0.1*ms"
+        inh.delay = "(1 + int(rand()*20)) * 0.1*ms"
+    else:
+        exc.delay = D
+        inh.delay = D
+    objs = dict(neurons=neurons, exc=exc, inh=inh)
+    if not deterministic:
+        objs["drive"] = b.PoissonInput(target=neurons, target_var="v", N=C_ext, rate=nu_ext, weight=J)
+    if monitor:
+        objs["spikes"] = b.SpikeMonitor(neurons)
+        objs["rate"] = b.PopulationRateMonitor(neurons)
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("neurons", "v")]
+    return objs
+
+
+def stdp(b, N=1000, duration=0.2, seed=99, raster_seed=7, monitor=True):
+    """Song-Abbott STDP (examples/synapses/STDP.py:30-62).  The Poisson input is replaced by a
+    pre-drawn raster fed through a SpikeGeneratorGroup-free deterministic source: a group whose
+    threshold compares against a pre-drawn per-neuron phase, so the run is deterministic."""
+    b.seed(seed)
+    ms, mV, Hz = b.ms, b.mV, b.Hz
+    taum = 10 * ms; taupre = 20 * ms; taupost = taupre  # noqa: E702
+    Ee = 0 * mV; vt = -54 * mV; vr = -60 * mV; El = -74 * mV; taue = 5 * ms  # noqa: E702
+    gmax = .01
+    dApre = .01
+    dApost = -dApre * taupre / taupost * 1.05
+    dApost *= gmax
+    dApre *= gmax
+    ns = dict(taum=taum, taupre=taupre, taupost=taupost, Ee=Ee, vt=vt, vr=vr, El=El, taue=taue,
+              gmax=gmax, dApre=dApre, dApost=dApost)
+    # deterministic regular-firing inputs with heterogeneous periods (15 Hz mean)
+    rng = np.random.RandomState(raster_seed)
+    inp = b.NeuronGroup(N, "dx/dt = rate : 1\nrate : Hz", threshold="x > 1", reset="x = 0",
+                        method="euler", name="inputs")
+    inp.rate = rng.uniform(5, 25, N) * Hz
+    inp.x = rng.uniform(0, 1, N)
+    neurons = b.NeuronGroup(1, """dv/dt = (ge * (Ee-v) + El - v) / taum : volt
+                                  dge/dt = -ge / taue : 1""",
+                            threshold="v>vt", reset="v = vr", method="euler", namespace=ns)
+    neurons.v = vr
+    S = b.Synapses(inp, neurons,
+                   """w : 1
+                      dApre/dt = -Apre / taupre : 1 (event-driven)
+                      dApost/dt = -Apost / taupost : 1 (event-driven)""",
+                   on_pre="""ge += w
+                             Apre += dApre
+                             w = clip(w + Apost, 0, gmax)""",
+                   on_post="""Apost += dApost
+                              w = clip(w + Apre, 0, gmax)""", namespace=ns)
+    S.connect()
+    S.w = "rand() * gmax"
+    objs = dict(inp=inp, neurons=neurons, S=S)
+    if monitor:
+        objs["spikes"] = b.SpikeMonitor(neurons)
+        objs["in_spikes"] = b.SpikeMonitor(inp)
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("S", "w"), ("neurons", "v"), ("neurons", "ge")]
+    return objs
+
+
+def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, delay_steps=0):
+    """Propagation stress test (brian2/tests/features/speed.py:263-326 `SynapsesOnly`): M source
+    neurons that spike every step, N targets, `w += 1.0` per event."""
+    b.seed(seed)
+    dt = float(b.defaultclock.dt)
+    M = max(1, int(rate_hz * N * dt))
+    G = b.NeuronGroup(M, "v:1", threshold="True", name="sources")
+    H = b.NeuronGroup(N, "w:1", name="targets")
+    S = b.Synapses(G, H, on_pre="w += 1.0")
+    S.connect(True, p=p)
+    if delay_steps:
+        S.delay = delay_steps * b.defaultclock.dt
+    objs = dict(G=G, H=H, S=S)
+    objs["net"] = b.Network(G, H, S)
+    objs["duration"] = duration
+    objs["state"] = [("H", "w")]
+    return objs
+
+
+MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=synapses_only)
+
+
+def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):
+    """Build + run ``name`` on ``device_name``; returns (objs, results dict of numpy arrays)."""
+    b.device.reinit()
+    b.device.activate()
+    b.set_device(device_name, directory=directory, build_on_run=False)
+    b.prefs.codegen.cpp.extra_compile_args_gcc = list(STRICT_GCC_FLAGS)
+    b.prefs.devices.cpp_standalone.openmp_threads = 0
+    if prefs_update:
+        for k, v in prefs_update.items():
+            b.prefs[k] = v
+    b.defaultclock.dt = 0.1 * b.ms
+    objs = MODELS[name](b, **model_kwds)
+    net = objs["net"]
+    net.run(objs["duration"] * b.second, namespace={})
+    b.device.build(directory=directory, compile=True, run=True, with_output=False, **(build_kwds or {}))
+    res = collect_results(b, objs)
+    return objs, res
+
+
+def collect_results(b, objs):
+    res = {}
+    for key, obj in objs.items():
+        if isinstance(obj, b.SpikeMonitor):
+            res[f"{key}_i"] = np.asarray(obj.i[:]).astype(np.int32)
+            res[f"{key}_t"] = np.asarray(obj.t_[:]).astype(np.float64)
+            res[f"{key}_count"] = np.asarray(obj.count[:]).astype(np.int32)
+        elif isinstance(obj, b.StateMonitor):
+            for var in obj.record_variables:
+                res[f"{key}_{var}"] = np.asarray(getattr(obj, var + "_")[:]).astype(np.float64)
+            res[f"{key}_t"] = np.asarray(obj.t_[:]).astype(np.float64)
+        elif isinstance(obj, b.PopulationRateMonitor):
+            res[f"{key}_rate"] = np.asarray(obj.rate_[:]).astype(np.float64)
+    for group, var in objs["state"]:
+        res[f"{group}_{var}"] = np.asarray(getattr(objs[group], var + "_")[:]).copy()
+    for key, obj in objs.items():
+        if isinstance(obj, b.Synapses):
+            res[f"{key}_nsyn"] = np.array([len(obj)], dtype=np.int64)
+    res["last_run_time"] = np.array([b.device._last_run_time])
+    return res

@@ -1,0 +1,53 @@
+"""Parity of the b200 device against golden vectors produced by the reference's cpp_standalone
+device (tests/golden/make_golden.py; strict flags, serial).  Spike trains must be identical on
+the deterministic fp64 configurations; state variables within rtol 1e-9 (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+
+import models
+from golden.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+#: state tolerance stated by BASELINE.json for fp64
+RTOL = 1e-9
+
+
+def _check(case, res, exact_state):
+    gold = np.load(os.path.join(GOLDEN, f"{case}.npz"))
+    for key in gold.files:
+        g, r = gold[key], res[key]
+        assert g.shape == r.shape, f"{case}:{key} shape {r.shape} != golden {g.shape}"
+        if g.dtype.kind in "iu" or key.endswith("_t"):
+            assert np.array_equal(g, r), f"{case}:{key} differs from the reference"
+        elif exact_state:
+            assert np.array_equal(g, r), f"{case}:{key} not bit-identical"
+        else:
+            np.testing.assert_allclose(r, g, rtol=RTOL, atol=1e-15, err_msg=f"{case}:{key}")
+
+
+@pytest.mark.parametrize("case,exact_state", [
+    ("cuba_4000", True),
+    ("cuba_1000", True),
+    ("brunel_homog", True),
+    ("brunel_hetero", True),
+    ("synapses_only", True),
+    ("synapses_only_delay", True),
+])
+def test_spike_exact_persistent(brian, project_dir, case, exact_state):
+    model, kwds = CASES[case]
+    objs, res = models.run_model(brian, model, "b200", project_dir, **kwds)
+    _check(case, res, exact_state)
+
+
+@pytest.mark.parametrize("case", ["cuba_1000", "brunel_hetero"])
+def test_spike_exact_stepwise(brian, project_dir, case):
+    """Same results when every code object is launched as its own kernel (no persistent kernel)."""
+    model, kwds = CASES[case]
+    objs, res = models.run_model(brian, model, "b200", project_dir,
+                                 prefs_update={"devices.b200.persistent": False}, **kwds)
+    _check(case, res, True)
+    brian.prefs["devices.b200.persistent"] = True
