@@ -13,16 +13,26 @@ REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(REPO_ROOT, "oracle", "_ref")
 
 
+def _select_host_compiler():
+    """Generated host code is compiled with the system g++ (shared libstdc++).  The image's
+    default CXX (/opt/gcc/bin/g++) links libstdc++ statically -- which crashes in iostream locale
+    code once the library is dlopen()ed into Python -- and cannot link -fopenmp."""
+    if os.environ.get("B200_KEEP_CXX"):
+        return
+    if os.path.exists("/usr/bin/g++"):
+        os.environ["CXX"] = "/usr/bin/g++"
+    if os.path.exists("/usr/bin/gcc"):
+        os.environ["CC"] = "/usr/bin/gcc"
+
+
 def ensure_brian2_importable():
+    _select_host_compiler()
     if "brian2" in sys.modules:
         return
     if importlib.util.find_spec("brian2") is not None:
         return
     if os.path.isdir(os.path.join(REF_DIR, "brian2")):
         sys.path.insert(0, REF_DIR)
-        # host-side C++ (synapse creation etc.) must be built with a g++ that can link OpenMP
-        os.environ.setdefault("CXX", "/usr/bin/g++")
-        os.environ.setdefault("CC", "/usr/bin/gcc")
         return
     raise ImportError(
         "brian2 is not importable and oracle/_ref is not populated; run "

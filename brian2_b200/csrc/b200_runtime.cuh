@@ -120,6 +120,12 @@ __device__ __forceinline__ void compact_owned(unsigned long long mask, int niter
     const int warp = threadIdx.x >> 5;
     const Slice sl = owned_slice(N, c);
 
+    // Only CTAs that own elements take part (for small groups most of the grid has nothing to
+    // compact and must not pay the look-back latency); the last owning CTA writes the count.
+    const int64_t chunk = owned_chunk(N, c.nb);
+    const int nact = (int)((N + chunk - 1) / chunk);
+    if (c.bid >= nact) return;
+
     // 1. per-warp totals
     int mine = __popcll(mask);
     int wtotal = mine;
@@ -136,7 +142,7 @@ __device__ __forceinline__ void compact_owned(unsigned long long mask, int niter
         if (w < warp) woff += v;
         ctotal += v;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && c.bid + 1 < nact) {
         st_release_u64(&ws[c.bid], ((unsigned long long)epoch << 32) | (unsigned int)ctotal);
     }
 
@@ -158,7 +164,7 @@ __device__ __forceinline__ void compact_owned(unsigned long long mask, int niter
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) b += s_pred[w];
         s_base = b;
-        if (c.bid == c.nb - 1) eventspace[N] = b + ctotal;
+        if (c.bid == nact - 1) eventspace[N] = b + ctotal;
     }
     __syncthreads();
 

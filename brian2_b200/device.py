@@ -649,6 +649,7 @@ class B200Device(CPPStandaloneDevice):
 
     def nvcc_flags(self):
         flags = [prefs.devices.b200.arch_flags] + list(prefs.devices.b200.extra_nvcc_flags)
+        flags += ["-ccbin", os.environ.get("CXX", "g++")]
         flags.append("-fmad=true" if prefs.devices.b200.fmad else "-fmad=false")
         if prefs.core.default_float_dtype == np.float32:
             flags.append("-DB200_FLOAT32")

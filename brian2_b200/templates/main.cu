@@ -37,6 +37,18 @@ extern int _b200_grid_override;
 
 static std::string _b200_error;
 
+#include <execinfo.h>
+#include <unistd.h>
+static void _b200_crash_handler(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "b200: fatal signal inside the project library, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1)) {}
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 void set_from_command_line(const std::vector<std::string> args)
 {
     for (const auto& arg : args) {
@@ -81,6 +93,11 @@ extern "C" {
 
 int b200_run_main(int argc, const char** argv)
 {
+    if (getenv("B200_DEBUG")) {
+        std::signal(SIGSEGV, _b200_crash_handler);
+        std::signal(SIGBUS, _b200_crash_handler);
+        std::signal(SIGFPE, _b200_crash_handler);
+    }
     try {
         _b200_error.clear();
         std::vector<std::string> args;

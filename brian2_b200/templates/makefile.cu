@@ -10,8 +10,8 @@ CU_OBJS = ${CU_SRCS:.cu=.o}
 NVCC = {{nvcc}}
 CUDA_HOME = {{cuda_home}}
 OPTIMISATIONS = {{ compiler_flags }}
-CXXFLAGS = -c -fPIC -Wno-write-strings $(OPTIMISATIONS) -I. -I$(CUDA_HOME)/include {{ compiler_debug_flags }}
-NVCCFLAGS = -c {{ nvcc_flags }} -I. -Xcompiler -fPIC {{ compiler_debug_flags }}
+CXXFLAGS = -c -fPIC -fno-gnu-unique -Wno-write-strings $(OPTIMISATIONS) -I. -I$(CUDA_HOME)/include {{ compiler_debug_flags }}
+NVCCFLAGS = -c {{ nvcc_flags }} -I. -Xcompiler -fPIC,-fno-gnu-unique {{ compiler_debug_flags }}
 LFLAGS = -shared -fPIC {{ linker_flags }} {{ linker_debug_flags }} -L$(CUDA_HOME)/lib64 -lcudart_static -lpthread -ldl -lrt
 
 all: $(LIBRARY)

@@ -24,20 +24,20 @@ def cuba(b, N=4000, p=0.02, duration=0.2, seed=1234, monitor=True):
     dgi/dt = -gi/taui : volt
     """
     P = b.NeuronGroup(N, eqs, threshold="v>Vt", reset="v = Vr", refractory=5 * ms, method="exact",
-                      namespace=dict(taum=taum, taue=taue, taui=taui, Vt=Vt, Vr=Vr, El=El))
+                      name="cuba_P", namespace=dict(taum=taum, taue=taue, taui=taui, Vt=Vt, Vr=Vr, El=El))
     P.v = "Vr + rand() * (Vt - Vr)"
     P.ge = 0 * mV
     P.gi = 0 * mV
     we = (60 * 0.27 / 10) * mV
     wi = (-20 * 4.5 / 10) * mV
     Ne = int(0.8 * N)
-    Ce = b.Synapses(P, P, on_pre="ge += we", namespace=dict(we=we))
-    Ci = b.Synapses(P, P, on_pre="gi += wi", namespace=dict(wi=wi))
+    Ce = b.Synapses(P, P, on_pre="ge += we", namespace=dict(we=we), name="cuba_Ce")
+    Ci = b.Synapses(P, P, on_pre="gi += wi", namespace=dict(wi=wi), name="cuba_Ci")
     Ce.connect(f"i<{Ne}", p=p)
     Ci.connect(f"i>={Ne}", p=p)
     objs = dict(P=P, Ce=Ce, Ci=Ci)
     if monitor:
-        objs["spikes"] = b.SpikeMonitor(P)
+        objs["spikes"] = b.SpikeMonitor(P, name="cuba_spikes")
     net = b.Network(*objs.values())
     objs["net"] = net
     objs["duration"] = duration
@@ -73,12 +73,12 @@ def cobahh(b, N=4000, duration=0.1, seed=1234, monitor=True, n_syn_per_neuron=80
     beta_n = .5*exp((10*mV-v+VT)/(40*mV))/ms : Hz
     """)
     P = b.NeuronGroup(N, model=eqs, threshold="v>-20*mV", refractory=3 * ms,
-                      method="exponential_euler", namespace=ns)
+                      method="exponential_euler", namespace=ns, name="hh_P")
     Ne = int(0.8 * N)
     Pe = P[:Ne]
     Pi = P[Ne:]
-    Ce = b.Synapses(Pe, P, on_pre="ge+=we", namespace=ns)
-    Ci = b.Synapses(Pi, P, on_pre="gi+=wi", namespace=ns)
+    Ce = b.Synapses(Pe, P, on_pre="ge+=we", namespace=ns, name="hh_Ce")
+    Ci = b.Synapses(Pi, P, on_pre="gi+=wi", namespace=ns, name="hh_Ci")
     Ce.connect(p=n_syn_per_neuron / N)
     Ci.connect(p=n_syn_per_neuron / N)
     P.v = "El + (randn() * 5 - 5)*mV"
@@ -86,9 +86,9 @@ def cobahh(b, N=4000, duration=0.1, seed=1234, monitor=True, n_syn_per_neuron=80
     P.gi = "(randn() * 12 + 20) * 10.*nS"
     objs = dict(P=P, Ce=Ce, Ci=Ci)
     if monitor:
-        objs["spikes"] = b.SpikeMonitor(P)
+        objs["spikes"] = b.SpikeMonitor(P, name="hh_spikes")
         if trace:
-            objs["trace"] = b.StateMonitor(P, "v", record=[t for t in trace if t < N])
+            objs["trace"] = b.StateMonitor(P, "v", record=[t for t in trace if t < N], name="hh_trace")
     objs["net"] = b.Network(*objs.values())
     objs["duration"] = duration
     objs["state"] = [("P", "v"), ("P", "ge"), ("P", "gi"), ("P", "m"), ("P", "n"), ("P", "h")]
@@ -116,10 +116,10 @@ def brunel(b, N_E=800, gamma=0.25, epsilon=0.1, duration=0.1, seed=4321, hetero_
     else:
         eqs = "dv/dt = -v/tau : volt (unless refractory)"
     neurons = b.NeuronGroup(N, eqs, threshold="v > theta", reset="v = V_r", refractory=tau_rp,
-                            method="exact", namespace=ns)
+                            method="exact", namespace=ns, name="brunel_neurons")
     neurons.v = "rand() * theta"
-    exc = b.Synapses(neurons[:N_E], neurons, on_pre="v += J", namespace=ns)
-    inh = b.Synapses(neurons[N_E:], neurons, on_pre="v += -g*J", namespace=ns)
+    exc = b.Synapses(neurons[:N_E], neurons, on_pre="v += J", namespace=ns, name="brunel_exc")
+    inh = b.Synapses(neurons[N_E:], neurons, on_pre="v += -g*J", namespace=ns, name="brunel_inh")
     exc.connect(p=epsilon)
     inh.connect(p=epsilon)
     if hetero_delays:
@@ -130,10 +130,11 @@ def brunel(b, N_E=800, gamma=0.25, epsilon=0.1, duration=0.1, seed=4321, hetero_
         inh.delay = D
     objs = dict(neurons=neurons, exc=exc, inh=inh)
     if not deterministic:
-        objs["drive"] = b.PoissonInput(target=neurons, target_var="v", N=C_ext, rate=nu_ext, weight=J)
+        objs["drive"] = b.PoissonInput(target=neurons, target_var="v", N=C_ext, rate=nu_ext, weight=J,
+                                       name="brunel_drive")
     if monitor:
-        objs["spikes"] = b.SpikeMonitor(neurons)
-        objs["rate"] = b.PopulationRateMonitor(neurons)
+        objs["spikes"] = b.SpikeMonitor(neurons, name="brunel_spikes")
+        objs["rate"] = b.PopulationRateMonitor(neurons, name="brunel_rate")
     objs["net"] = b.Network(*objs.values())
     objs["duration"] = duration
     objs["state"] = [("neurons", "v")]
@@ -158,12 +159,13 @@ def stdp(b, N=1000, duration=0.2, seed=99, raster_seed=7, monitor=True):
     # deterministic regular-firing inputs with heterogeneous periods (15 Hz mean)
     rng = np.random.RandomState(raster_seed)
     inp = b.NeuronGroup(N, "dx/dt = rate : 1\nrate : Hz", threshold="x > 1", reset="x = 0",
-                        method="euler", name="inputs")
+                        method="euler", name="stdp_inputs")
     inp.rate = rng.uniform(5, 25, N) * Hz
     inp.x = rng.uniform(0, 1, N)
     neurons = b.NeuronGroup(1, """dv/dt = (ge * (Ee-v) + El - v) / taum : volt
                                   dge/dt = -ge / taue : 1""",
-                            threshold="v>vt", reset="v = vr", method="euler", namespace=ns)
+                            threshold="v>vt", reset="v = vr", method="euler", namespace=ns,
+                            name="stdp_neurons")
     neurons.v = vr
     S = b.Synapses(inp, neurons,
                    """w : 1
@@ -173,13 +175,13 @@ def stdp(b, N=1000, duration=0.2, seed=99, raster_seed=7, monitor=True):
                              Apre += dApre
                              w = clip(w + Apost, 0, gmax)""",
                    on_post="""Apost += dApost
-                              w = clip(w + Apre, 0, gmax)""", namespace=ns)
+                              w = clip(w + Apre, 0, gmax)""", namespace=ns, name="stdp_S")
     S.connect()
     S.w = "rand() * gmax"
     objs = dict(inp=inp, neurons=neurons, S=S)
     if monitor:
-        objs["spikes"] = b.SpikeMonitor(neurons)
-        objs["in_spikes"] = b.SpikeMonitor(inp)
+        objs["spikes"] = b.SpikeMonitor(neurons, name="stdp_spikes")
+        objs["in_spikes"] = b.SpikeMonitor(inp, name="stdp_in_spikes")
     objs["net"] = b.Network(*objs.values())
     objs["duration"] = duration
     objs["state"] = [("S", "w"), ("neurons", "v"), ("neurons", "ge")]
@@ -192,9 +194,9 @@ def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, dela
     b.seed(seed)
     dt = float(b.defaultclock.dt)
     M = max(1, int(rate_hz * N * dt))
-    G = b.NeuronGroup(M, "v:1", threshold="True", name="sources")
-    H = b.NeuronGroup(N, "w:1", name="targets")
-    S = b.Synapses(G, H, on_pre="w += 1.0")
+    G = b.NeuronGroup(M, "v:1", threshold="True", name="so_sources")
+    H = b.NeuronGroup(N, "w:1", name="so_targets")
+    S = b.Synapses(G, H, on_pre="w += 1.0", name="so_S")
     S.connect(True, p=p)
     if delay_steps:
         S.delay = delay_steps * b.defaultclock.dt
@@ -209,7 +211,15 @@ MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=
 
 
 def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):
-    """Build + run ``name`` on ``device_name``; returns (objs, results dict of numpy arrays)."""
+    """Build + run ``name`` on ``device_name``; returns (objs, results dict of numpy arrays).
+
+    All objects carry explicit names: Brian orders code objects of the same schedule slot by
+    (order, name) (core/network.py:907-909), so auto-generated names (`synapses_1`, ...) would
+    make e.g. the excitatory/inhibitory delivery order -- and with it the last bits of `v` --
+    depend on how many objects the process created before."""
+    import gc
+
+    gc.collect()
     b.device.reinit()
     b.device.activate()
     b.set_device(device_name, directory=directory, build_on_run=False)

@@ -36,6 +36,11 @@ def _check(case, res, exact_state):
     ("brunel_hetero", True),
     ("synapses_only", True),
     ("synapses_only_delay", True),
+    # exponential_euler evaluates exp/expm1 per neuron on the device (CUDA libm, <= 1-2 ulp from
+    # glibc): spikes must still be identical over this horizon, state within rtol 1e-9
+    ("cobahh_1000", False),
+    # per-synapse weights are accumulated with fp64 atomics (order not deterministic)
+    ("stdp_1000", False),
 ])
 def test_spike_exact_persistent(brian, project_dir, case, exact_state):
     model, kwds = CASES[case]
