@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the b200 Brian2 device.
+
+Metric (BASELINE.json): synaptic events/s (and the sim-time realtime factor) of the
+per-timestep hot loop on the named synthetic networks.  Default workload = BASELINE.json
+configs[1]: COBAHH (examples/COBAHH.py equations) scaled to 256k neurons, 80 synapses per neuron,
+exponential_euler, fp64, SpikeMonitor + 3 voltage traces.
+
+A bench "step" is one ``run(T)`` call of the Brian2 script, i.e. ``--sim-steps`` simulation
+timesteps (dt = 0.1 ms) of the whole network: upload of all arrays (host -> device), the step
+loop inside the persistent kernel, download of the written arrays.
+
+* ``value``   events/s over the K timed steps with all inputs resident in HBM: CUDA-event time of
+              the step loops only (the reference excludes its file I/O in the same way,
+              templates/network.cpp:51,106-114).
+* ``e2e``     the same events divided by upload + loop + download of every timed step, i.e. what a
+              user of ``set_device('b200')`` observes per ``run()`` call, host buffers in and out.
+* ``--impl reference``  the UNMODIFIED reference (``cpp_standalone`` + OpenMP on all host cores,
+              default reference flags) on the same network, a bounded number of timesteps per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (model, kwargs, bytes per neuron-step, bytes per synaptic event)   [SURVEY.md 8d]
+    "cobahh_256k": ("cobahh", dict(N=256000), 105.0, 20.0),
+    "cobahh_4k": ("cobahh", dict(N=4000), 105.0, 20.0),
+    "cuba_4k": ("cuba", dict(N=4000, p=0.02), 58.0, 20.0),
+    "cuba_256k": ("cuba", dict(N=256000, p=80.0 / 256000), 58.0, 20.0),
+    "brunel_100k": ("brunel", dict(N_E=80000, epsilon=0.01, deterministic=True), 33.0, 20.0),
+}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._reader, daemon=True).start()
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [s for (ts, s) in self.samples if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.2)]
+        if not rows:
+            rows = [s for (_, s) in self.samples]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, parts[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _import_brian():
+    import brian2_b200  # noqa: F401
+    import brian2 as b
+
+    return b
+
+
+def _build_script(b, workload, device_name, directory, sim_steps, n_runs, openmp_threads=0, strict=True):
+    import models
+
+    model, kwds, _, _ = WORKLOADS[workload]
+    import gc
+
+    gc.collect()
+    b.device.reinit()
+    b.device.activate()
+    b.set_device(device_name, directory=directory, build_on_run=False)
+    if strict:
+        b.prefs.codegen.cpp.extra_compile_args_gcc = list(models.STRICT_GCC_FLAGS)
+    else:  # the reference's own default flags (codegen/cpp_prefs.py:109-116)
+        b.prefs.codegen.cpp.extra_compile_args_gcc = ["-w", "-O3", "-ffast-math", "-fno-finite-math-only",
+                                                      "-march=native", "-std=c++17"]
+    b.prefs.devices.cpp_standalone.openmp_threads = openmp_threads
+    b.defaultclock.dt = 0.1 * b.ms
+    objs = models.MODELS[model](b, duration=0.0, **kwds)
+    net = objs["net"]
+    T = sim_steps * 1e-4
+    for r in range(n_runs):
+        net.run(T * b.second, namespace={})
+        if device_name == "cpp_standalone":
+            b.device.insert_code(
+                "main", 'std::cout << "B200BENCH_RUN " << Network::_last_run_time << std::endl;')
+    return objs
+
+
+def _outdegree_events(b, objs, t_from):
+    """Synaptic events in [t_from, end): sum over recorded spikes of the out-degree of the
+    spiking neuron over every pathway listening to it."""
+    import numpy as np
+
+    spikes = objs["spikes"]
+    i = np.asarray(spikes.i[:])
+    t = np.asarray(spikes.t_[:])
+    sel = i[t >= t_from - 1e-12]
+    n = len(objs["spikes"].source)
+    out = np.zeros(n, dtype=np.int64)
+    for obj in objs.values():
+        if isinstance(obj, b.Synapses):
+            pre = np.asarray(obj.i[:]) + getattr(obj.source, "start", 0)
+            out += np.bincount(pre, minlength=n)
+    return float(out[sel].sum()), int(len(sel))
+
+
+def run_b200(args, rank, world):
+    b = _import_brian()
+    sim_steps = args.sim_steps or 500
+    n_runs = args.warmup + args.steps
+    directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
+    t_build0 = time.time()
+    objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs)
+    b.device.build(directory=directory, compile=True, run=False, with_output=False)
+    build_seconds = time.time() - t_build0
+
+    _barrier(world)
+    sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    t0 = time.time()
+    b.device.run(directory=directory, with_output=False)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    cnt = b.device.counter
+    runs = int(cnt("runs"))
+    assert runs == n_runs, (runs, n_runs)
+    timed = range(args.warmup, n_runs)
+    dev_s = sum(cnt(f"run{r}.device_seconds") for r in timed)
+    e2e_s = sum(cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds") + cnt(f"run{r}.download_seconds")
+                for r in timed)
+    events = sum(cnt(f"run{r}.events") for r in timed)
+    steps = sum(cnt(f"run{r}.steps") for r in timed)
+    persistent = all(cnt(f"run{r}.persistent") == 1 for r in timed)
+    model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
+    n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
+    n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
+    return dict(dev_s=dev_s, e2e_s=e2e_s, events=events, timesteps=steps, persistent=persistent,
+                h2d=cnt("h2d_bytes") / n_runs, d2h=cnt("d2h_bytes") / n_runs, launches=cnt("launches"),
+                clocks=clocks, n_neurons=n_neurons, n_syn=n_syn, build_seconds=build_seconds,
+                sim_steps=sim_steps, bytes_neuron=bytes_neuron, bytes_event=bytes_event,
+                spikes=len(objs["spikes"].i[:]) if "spikes" in objs else None)
+
+
+def run_reference(args, sim_steps, warmup, steps, threads, strict=False):
+    """The reference's own CPU implementation of the path (cpp_standalone [+ OpenMP])."""
+    b = _import_brian()
+    n_runs = warmup + steps
+    directory = tempfile.mkdtemp(prefix="b200_bench_ref_")
+    objs = _build_script(b, args.workload, "cpp_standalone", directory, sim_steps, n_runs,
+                         openmp_threads=threads, strict=strict)
+    b.device.build(directory=directory, compile=True, run=True, with_output=False)
+    with open(os.path.join(b.device.results_dir, "stdout.txt")) as f:
+        times = [float(line.split()[1]) for line in f if line.startswith("B200BENCH_RUN")]
+    assert len(times) == n_runs, (times, n_runs)
+    loop_s = sum(times[warmup:])
+    events, nspikes = _outdegree_events(b, objs, warmup * sim_steps * 1e-4)
+    n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
+    return dict(loop_s=loop_s, events=events, timesteps=steps * sim_steps, n_neurons=n_neurons,
+                spikes=nspikes)
+
+
+def _dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    return rank, world
+
+
+_PG = {"init": False}
+
+
+def _barrier(world):
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    if not _PG["init"]:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        _PG["init"] = True
+    dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _allreduce(values, op, world):
+    if world <= 1:
+        return values
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+    return t.tolist()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cobahh_256k", choices=sorted(WORKLOADS))
+    ap.add_argument("--sim-steps", type=int, default=0, help="simulation timesteps per bench step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = _dist()
+    hbm_peak, peak_src = _peaks()
+    model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
+    config = {
+        "workload": f"{args.workload}: {model} {kwds}, dt=0.1ms, fp64, SpikeMonitor(+3 v traces for COBAHH)",
+        "connectivity": "reference Synapses.connect (host, mt19937), identical on both arms",
+        "l2": "working set (state + CSR) is comparable to the 126 MB L2 by nature of the workload; "
+              "every timed step starts after a fresh H2D upload of all arrays, no explicit flush",
+    }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        sim_steps = args.sim_steps or 500
+        r = run_reference(args, sim_steps, args.warmup, args.steps, threads, strict=False)
+        value = r["events"] / r["loop_s"]
+        config["timesteps_per_step"] = sim_steps
+        line = {
+            "impl": "reference", "metric": "synaptic_events_per_s", "value": value, "unit": "events/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * r["loop_s"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "realtime_factor": r["timesteps"] * 1e-4 / r["loop_s"],
+            "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "reference",
+                             "sample": f"{args.steps} x {sim_steps} timesteps of the same network, "
+                                       f"cpp_standalone + OpenMP({threads}), reference default flags"},
+            "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    r = run_b200(args, rank, world)
+    # whole-job numbers: max time over ranks, events summed over ranks
+    dev_s, e2e_s = _allreduce([r["dev_s"], r["e2e_s"]], "MAX", world)
+    events, = _allreduce([r["events"]], "SUM", world)
+    if rank != 0:
+        return
+    value = events / dev_s
+    e2e_value = events / e2e_s
+    timesteps = r["timesteps"]
+    algo_bytes = timesteps * r["n_neurons"] * bytes_neuron + r["events"] * bytes_event
+    achieved = algo_bytes / r["dev_s"] / 1e9
+    config.update({
+        "timesteps_per_step": r["sim_steps"], "neurons": r["n_neurons"], "synapses": r["n_syn"],
+        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+        "execution": "persistent cooperative step kernel" if r["persistent"] else "one launch per code object",
+        "build_seconds": round(r["build_seconds"], 1),
+    })
+    line = {
+        "metric": "synaptic_events_per_s", "value": value, "unit": "events/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config,
+        "realtime_factor": timesteps * 1e-4 / r["dev_s"],
+        "us_per_timestep": 1e6 * r["dev_s"] / max(timesteps, 1),
+        "clocks": r["clocks"],
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": r["h2d"],
+                "d2h_bytes_per_step": r["d2h"]},
+        "gpu_launches": int(r["launches"]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "persistent step kernel (stateupdate+threshold+propagation+monitors)",
+                     "algorithmic_bytes": f"{bytes_neuron} B/neuron-step + {bytes_event} B/event"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ref_steps = 50 if "256k" in args.workload else 2000
+        try:
+            ref = run_reference(args, ref_steps, 1, 2, threads, strict=False)
+            line["cpu_baseline"] = {
+                "value": ref["events"] / ref["loop_s"], "unit": "events/s", "cores": threads,
+                "kind": "reference",
+                "sample": f"2 x {ref_steps} timesteps (after 1 warm-up) of the same network on "
+                          f"cpp_standalone + OpenMP({threads}), reference default flags",
+                "realtime_factor": ref["timesteps"] * 1e-4 / ref["loop_s"],
+            }
+        except Exception as ex:  # the baseline must never hide the measurement
+            line["cpu_baseline"] = {"value": None, "unit": "events/s", "cores": threads, "kind": "reference",
+                                    "sample": f"failed: {ex}"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -608,6 +608,13 @@ class B200Device(CPPStandaloneDevice):
                     plan["n_barriers"] = 1 + sum(1 for it in items if it["barrier"])
                 except NotImplementedError as ex:
                     logger.warn(f"run #{index} falls back to stepwise execution: {ex}")
+            # run() calls with an identical schedule share one kernel
+            plan["alias"] = None
+            if plan["clock"]:
+                for other in plans:
+                    if other["clock"] == plan["clock"] and other["signature"] == plan["signature"] and other["alias"] is None:
+                        plan["alias"] = other["index"]
+                        break
             plans.append(plan)
         self._b200_plan_info = plans
         user_headers = self.headers + prefs["codegen.cpp.headers"]

@@ -71,7 +71,10 @@ static int _b200_grid_for(const void* kernel)
 {% endfor %}
 
 {% for plan in plans %}
-{% if plan.clock %}
+{% if plan.clock and plan.alias is not none %}
+// run() call #{{plan.index}} has the same schedule as #{{plan.alias}}: shares its kernel
+const B200Plan _b200_plan_{{plan.index}} = { _b200_run_chunk_{{plan.alias}}, "{{plan.signature}}" };
+{% elif plan.clock %}
 // =============================================================================================
 // persistent step kernel for run() call #{{plan.index}}
 //   schedule: {{plan.signature}}

@@ -144,6 +144,25 @@ double b200_get_counter(const char* key)
     if (k == "download_seconds") return st.download_seconds;
     if (k == "device_bytes") return (double)st.bytes_allocated;
     if (k == "num_sms") return (double)st.num_sms;
+    if (k == "runs") return (double)Network::_b200_run_log.size();
+    // per-run records: "run<i>.<field>"
+    if (k.compare(0, 3, "run") == 0) {
+        const size_t dot = k.find('.');
+        if (dot != std::string::npos) {
+            const size_t i = (size_t)atoi(k.substr(3, dot - 3).c_str());
+            const std::string f = k.substr(dot + 1);
+            if (i < Network::_b200_run_log.size()) {
+                const B200RunRecord& r = Network::_b200_run_log[i];
+                if (f == "device_seconds") return r.device_seconds;
+                if (f == "wall_seconds") return r.wall_seconds;
+                if (f == "upload_seconds") return r.upload_seconds;
+                if (f == "download_seconds") return r.download_seconds;
+                if (f == "events") return r.events;
+                if (f == "steps") return (double)r.steps;
+                if (f == "persistent") return (double)r.persistent;
+            }
+        }
+    }
     return -1.0;
 }
 

@@ -24,6 +24,7 @@ bool Network::_globally_running = false;
 int Network::_b200_mode = 0;
 long long Network::_b200_max_chunk = 20000;
 long long Network::_b200_steps_run = 0;
+std::vector<B200RunRecord> Network::_b200_run_log;
 
 Network::Network() { t = 0.0; }
 
@@ -75,6 +76,14 @@ void Network::run(const double duration, void (*report_func)(const double, const
     // host mirrors -> device (not part of the timed loop, like the reference's _load_arrays)
     _b200_upload();
 
+    // device-side clock of the loop: CUDA events on the launching stream
+    static cudaEvent_t _ev_start = 0, _ev_stop = 0;
+    if (!_ev_start) { B200_CUDA(cudaEventCreate(&_ev_start)); B200_CUDA(cudaEventCreate(&_ev_stop)); }
+    const unsigned long long _events_before = _b200_events_delivered();
+    const long long _steps_before = Network::_b200_steps_run;
+    const double _upload_before = b200::state().upload_seconds;
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaEventRecord(_ev_start, b200::state().stream));
     hrc::time_point start = hrc::now(), current;
     if (report_func)
         report_func(0.0, 0.0, t_start, duration);
@@ -165,6 +174,7 @@ void Network::run(const double duration, void (*report_func)(const double, const
                 Network::_globally_stopped = true;
         }
     }
+    B200_CUDA(cudaEventRecord(_ev_stop, b200::state().stream));
     B200_CUDA(cudaStreamSynchronize(b200::state().stream));
     B200_CUDA(cudaDeviceSynchronize());
     Network::_globally_running = false;
@@ -183,7 +193,21 @@ void Network::run(const double duration, void (*report_func)(const double, const
         _last_run_completed_fraction = 1.0;
 
     // device -> host mirrors (written arrays only)
+    const double _download_before = b200::state().download_seconds;
     _b200_download();
+    {
+        B200RunRecord rec;
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, _ev_start, _ev_stop));
+        rec.device_seconds = 1e-3 * ms;
+        rec.wall_seconds = elapsed_realtime;
+        rec.steps = Network::_b200_steps_run - _steps_before;
+        rec.events = (double)(_b200_events_delivered() - _events_before);
+        rec.upload_seconds = b200::state().upload_seconds - _upload_before;
+        rec.download_seconds = b200::state().download_seconds - _download_before;
+        rec.persistent = persistent ? 1 : 0;
+        Network::_b200_run_log.push_back(rec);
+    }
 
     if (report_func)
         report_func(elapsed_realtime, _last_run_completed_fraction, t_start, duration);
@@ -206,6 +230,16 @@ struct B200Plan {
     const char* signature;
 };
 
+// one record per Network::run call (bench.py reads them through b200_get_counter)
+struct B200RunRecord {
+    double device_seconds;     // CUDA-event time of the step loop
+    double wall_seconds;       // host clock around the same region
+    double upload_seconds, download_seconds;
+    double events;             // synaptic events delivered during this run
+    long long steps;
+    int persistent;
+};
+
 class Network
 {
     std::set<BaseClock*> clocks, curclocks;
@@ -221,6 +255,7 @@ public:
     static int _b200_mode;              // 0: persistent kernel when possible, 1: always stepwise
     static long long _b200_max_chunk;   // steps per persistent launch
     static long long _b200_steps_run;
+    static std::vector<B200RunRecord> _b200_run_log;
 
     Network();
     void clear();

@@ -64,7 +64,9 @@ void b200_request_stop(void);
 int b200_set_option(const char* key, double value);
 
 /* Counters: "launches", "events" (delivered synaptic events), "steps", "h2d_bytes",
- * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms".  -1 if unknown. */
+ * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "runs", and per
+ * Network::run call "run<i>.device_seconds|wall_seconds|upload_seconds|download_seconds|events|
+ * steps|persistent".  -1 if unknown. */
 double b200_get_counter(const char* key);
 
 /* Per-code-object device seconds (profile mode).  Fills up to `cap` entries, returns the count.
