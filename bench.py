@@ -158,6 +158,7 @@ def run_b200(args, rank, world):
     n_runs = args.warmup + args.steps
     directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
     t_build0 = time.time()
+    b.prefs["devices.b200.persistent"] = not args.stepwise
     objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs)
     b.device.build(directory=directory, compile=True, run=False, with_output=False)
     build_seconds = time.time() - t_build0
@@ -250,6 +251,8 @@ def main():
     ap.add_argument("--workload", default="cobahh_256k", choices=sorted(WORKLOADS))
     ap.add_argument("--sim-steps", type=int, default=0, help="simulation timesteps per bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stepwise", action="store_true",
+                    help="profiling aid: one kernel launch per code object per step (not the product mode)")
     args = ap.parse_args()
     rank, world = _dist()
     hbm_peak, peak_src = _peaks()

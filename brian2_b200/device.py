@@ -156,10 +156,15 @@ class B200Device(CPPStandaloneDevice):
             )
         template_kwds = dict(template_kwds) if template_kwds is not None else {}
         if codeobj_class is B200CodeObject:
-            self._b200_stream_counter += 1
+            import zlib
+
             clock = getattr(owner, "clock", None)
             template_kwds["b200_clock"] = clock.name if clock is not None else "defaultclock"
-            template_kwds["b200_stream_id"] = self._b200_stream_counter
+            # RNG stream of a code object: stable across run() calls (the counter part of the
+            # generator carries the time step), distinct between code objects
+            template_kwds["b200_stream_id"] = zlib.crc32(
+                f"{owner.name}.{template_name}.{name.rstrip('*')}".encode()
+            )
             template_kwds["b200_template_name"] = template_name
         codeobj = super().code_object(
             owner,
@@ -354,6 +359,7 @@ class B200Device(CPPStandaloneDevice):
 
     def _collect_monitors(self):
         monitors = []
+        seen = set()
         for codeobj in self.code_objects.values():
             if not self.is_device_codeobj(codeobj):
                 continue
@@ -362,6 +368,10 @@ class B200Device(CPPStandaloneDevice):
             if template not in ("spikemonitor", "statemonitor", "ratemonitor"):
                 continue
             owner = info["owner"]
+            # every run() call creates a new code object for the same monitor
+            if owner.name in seen:
+                continue
+            seen.add(owner.name)
             kind = {"spikemonitor": "spike", "statemonitor": "state", "ratemonitor": "rate"}[template]
             buffers = []
             width = 1
@@ -574,6 +584,7 @@ class B200Device(CPPStandaloneDevice):
 
     def generate_codeobj_source(self, writer):
         device_objs = []
+        canonical, alias_of = {}, {}
         for codeobj in self.code_objects.values():
             host_consts = self._constant_lines(codeobj, device_side=False)
             for block in codeobj.before_after_blocks:
@@ -584,8 +595,15 @@ class B200Device(CPPStandaloneDevice):
                 dev_consts = self._constant_lines(codeobj, device_side=True)
                 code = codeobj.code.cpp_file.replace("%CONSTANTS_DEV%", dev_consts)
                 code = code.replace("%CONSTANTS%", host_consts)
-                writer.write(f"code_objects/{codeobj.name}.cuh", code)
-                device_objs.append(codeobj)
+                # Every run() call re-creates the code objects of all its objects: identical
+                # source (up to the name) is compiled once and shared.
+                key = code.replace(codeobj.name, "\0")
+                rep = canonical.setdefault(key, codeobj.name)
+                if rep != codeobj.name:
+                    alias_of[codeobj.name] = rep
+                else:
+                    writer.write(f"code_objects/{codeobj.name}.cuh", code)
+                    device_objs.append(codeobj)
             else:
                 code = codeobj.code.cpp_file.replace("%CONSTANTS%", host_consts)
                 writer.write(f"code_objects/{codeobj.name}.cpp", code)
@@ -600,6 +618,8 @@ class B200Device(CPPStandaloneDevice):
                 clock = next(iter(clocks))
                 try:
                     items = self._plan_barriers(entries)
+                    for it in items:
+                        it["name"] = alias_of.get(it["name"], it["name"])
                     plan["entries"] = items
                     plan["clock"] = clock.name
                     plan["signature"] = " ".join(
@@ -622,6 +642,7 @@ class B200Device(CPPStandaloneDevice):
             None,
             None,
             device_code_objects=device_objs,
+            code_object_aliases=sorted(alias_of.items()),
             plans=[p for p in plans],
             user_headers=user_headers,
             profiled=bool(self.enable_profiling_any),

@@ -69,6 +69,9 @@ static int _b200_grid_for(const void* kernel)
 {% for codeobj in device_code_objects %}
 #include "code_objects/{{codeobj.name}}.cuh"
 {% endfor %}
+{% for name, rep in code_object_aliases %}
+void _run_{{name}}() { _run_{{rep}}(); }   // same source as {{rep}} (created by a later run() call)
+{% endfor %}
 
 {% for plan in plans %}
 {% if plan.clock and plan.alias is not none %}
