@@ -16,6 +16,9 @@ ABI_SYMBOLS = [
     "b200_last_run_time",
     "b200_last_run_completed_fraction",
     "b200_request_stop",
+    "b200_set_comm",
+    "b200_comm_rank",
+    "b200_comm_world",
     "b200_set_option",
     "b200_get_counter",
     "b200_profiling",
@@ -24,6 +27,10 @@ ABI_SYMBOLS = [
     "b200_set_array",
     "b200_finalize",
 ]
+
+
+#: int allgather(const void* send, void* recv, size_t nbytes_per_rank)
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 
 class B200Library:
@@ -72,6 +79,11 @@ class B200Library:
         L.b200_set_array.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
         L.b200_set_array.restype = ctypes.c_int
         L.b200_finalize.restype = ctypes.c_int
+        L.b200_set_comm.argtypes = [ctypes.c_int, ctypes.c_int, ALLGATHER_FN]
+        L.b200_set_comm.restype = ctypes.c_int
+        L.b200_comm_rank.restype = ctypes.c_int
+        L.b200_comm_world.restype = ctypes.c_int
+        self._allgather_cb = None   # keeps the ctypes callback alive
 
     # ------------------------------------------------------------------------------------------
     def run_main(self, args, stdout=None):
@@ -90,6 +102,31 @@ class B200Library:
             if saved is not None:
                 os.dup2(saved, 1)
                 os.close(saved)
+
+    def set_comm(self, rank, world, allgather=None):
+        """Multi-GPU: ``allgather(bytes) -> list of bytes (one per rank)`` is a Python callable
+        (e.g. built on ``torch.distributed.all_gather_object``); it is only used outside the step
+        loop."""
+        cb = ALLGATHER_FN(0)
+        if allgather is not None:
+            def _cb(send, recv, nbytes):
+                try:
+                    parts = allgather(ctypes.string_at(send, nbytes))
+                    if len(parts) != world or any(len(p) != nbytes for p in parts):
+                        return 2
+                    ctypes.memmove(recv, b"".join(parts), nbytes * world)
+                    return 0
+                except Exception:   # never let an exception cross the C boundary
+                    import traceback
+
+                    traceback.print_exc()
+                    return 1
+
+            cb = ALLGATHER_FN(_cb)
+        self._allgather_cb = cb
+        status = self.lib.b200_set_comm(int(rank), int(world), cb)
+        if status != 0:
+            raise RuntimeError(f"b200_set_comm({rank}, {world}) failed with status {status}")
 
     def last_error(self):
         msg = self.lib.b200_last_error()

@@ -48,6 +48,8 @@ struct RuntimeState {
     size_t bytes_allocated = 0;
     unsigned long long seed = 0;
     bool seeded = false;
+    // multi-GPU plumbing: set through b200_set_comm (include/brian2_b200.h) before b200_run_main
+    int (*allgather)(const void* send, void* recv, size_t nbytes_per_rank) = nullptr;
     unsigned long long launches = 0;   // kernels launched inside run loops
     double upload_seconds = 0.0, download_seconds = 0.0;
     size_t h2d_bytes = 0, d2h_bytes = 0;
@@ -77,15 +79,12 @@ inline void runtime_init() {
     if (e != cudaSuccess || ndev == 0)
         throw std::runtime_error(
             "b200 device: no CUDA device available (this device has no CPU fallback)");
+    // one process per GPU: rank/world come from b200_set_comm; the device from LOCAL_RANK
     const char* lr = getenv("LOCAL_RANK");
-    const char* rk = getenv("RANK");
-    const char* ws = getenv("WORLD_SIZE");
-    const char* ng = getenv("B200_MULTI_GPU");
-    if (ng && atoi(ng) > 0 && ws && atoi(ws) > 1) {
-        s.world = atoi(ws);
-        s.rank = rk ? atoi(rk) : 0;
-    }
-    s.device = lr ? atoi(lr) % ndev : 0;
+    s.device = (s.world > 1 && lr) ? atoi(lr) % ndev : 0;
+    if (s.world > kMaxRanks) throw std::runtime_error("b200: at most 8 ranks (GPUs of one box)");
+    if (s.world > 1 && !s.allgather)
+        throw std::runtime_error("b200: world > 1 needs an allgather callback (b200_set_comm)");
     B200_CUDA(cudaSetDevice(s.device));
     cudaDeviceProp prop;
     B200_CUDA(cudaGetDeviceProperties(&prop, s.device));
@@ -148,49 +147,153 @@ inline void grow_buffer(T*& dev, size_t& cap, size_t used, size_t new_cap) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Event ring: the last `slots` spike lists of one event space, [slots][stride] int32, list s is
-// stored at slot (timestep % slots), ids ascending, count in the last element (same layout as
-// `_spikespace`, threshold.cpp:24-31).
+// host-side collectives over the callback (setup / teardown only, never inside the step loop)
 // ---------------------------------------------------------------------------------------------
-struct EventRing {
-    int32_t* dev = nullptr;
-    int slots = 0;
-    int stride = 0;            // N + 1
-    int required = 1;          // max delay + 1 over all pathways reading this event space
-    unsigned long long* scan_ws = nullptr;   // look-back workspace (kBlock entries)
+inline void host_allgather(const void* send, void* recv, size_t nbytes) {
+    RuntimeState& s = state();
+    if (s.world <= 1) { memcpy(recv, send, nbytes); return; }
+    if (s.allgather(send, recv, nbytes) != 0) throw std::runtime_error("b200: allgather callback failed");
+}
+inline void host_barrier() {
+    if (state().world <= 1) return;
+    char one = 1, all[kMaxRanks];
+    host_allgather(&one, all, 1);
+}
 
-    void require(int nslots) { required = std::max(required, nslots); }
+// ---------------------------------------------------------------------------------------------
+// Event space: the last `slots` spike lists of one group, as per-CTA segments and (a few steps
+// later) as the reference's compact `_spikespace` layout -- see EventSpaceDev in b200_types.h.
+// ---------------------------------------------------------------------------------------------
+struct EventSpace {
+    int32_t* seg = nullptr;
+    int32_t* compact = nullptr;
+    int32_t* seg_start = nullptr;
+    unsigned long long* done = nullptr;
+    int slots = 0, N = 0, nb = 0, nseg = 0, id = 0;
+    int max_delay = 0;         // over all pathways reading this event space
+    int min_delay = 1 << 30;   // ditto (1<<30: no pathway)
+    void* peer_seg[kMaxRanks] = {0};
+    void* peer_done[kMaxRanks] = {0};
+    bool peers_open = false;
 
-    // (re)allocate; keeps the history of the last min(slots, old slots) steps before `timestep`
-    void ensure(int stride_, int64_t timestep) {
-        if (!scan_ws) {
-            scan_ws = (unsigned long long*)dev_alloc(kBlock * sizeof(unsigned long long));
-            B200_CUDA(cudaMemset(scan_ws, 0, kBlock * sizeof(unsigned long long)));
+    void require(int dmin, int dmax) {
+        max_delay = std::max(max_delay, dmax);
+        min_delay = std::min(min_delay, dmin);
+    }
+    // On several GPUs a step is compacted only when a consumer can first need it (min delay - 1
+    // steps later), so that the wait for the peers' segments never stalls the step loop.
+    int lag() const {
+        if (state().world <= 1 || min_delay == (1 << 30)) return 0;
+        return std::max(0, min_delay - 1);
+    }
+    int required_slots() const { return 2 * (max_delay + 1) + 2; }
+
+    void close_peers() {
+        for (int q = 0; q < kMaxRanks; ++q) {
+            if (peer_seg[q] && q != state().rank) cudaIpcCloseMemHandle(peer_seg[q]);
+            if (peer_done[q] && q != state().rank) cudaIpcCloseMemHandle(peer_done[q]);
+            peer_seg[q] = peer_done[q] = nullptr;
         }
-        if (dev && slots >= required && stride == stride_) return;
-        const int new_slots = required;
-        int32_t* nd = (int32_t*)dev_alloc((size_t)new_slots * stride_ * sizeof(int32_t));
-        B200_CUDA(cudaMemset(nd, 0, (size_t)new_slots * stride_ * sizeof(int32_t)));
-        if (dev && stride == stride_) {
-            // the old ring holds steps timestep-1 ... timestep-slots
+        peers_open = false;
+    }
+
+    // (re)allocate; keeps the history of the last steps before `timestep`
+    void ensure(int N_, int nb_, int64_t timestep) {
+        RuntimeState& st = state();
+        const int need = required_slots();
+        if (seg && slots >= need && N == N_ && nb == nb_) return;
+        const int new_slots = need;
+        const int new_nseg = st.world * nb_;
+        const size_t seg_stride = (size_t)N_ + new_nseg;
+        int32_t* nseg_ = (int32_t*)dev_alloc((size_t)new_slots * seg_stride * sizeof(int32_t));
+        int32_t* ncomp = (int32_t*)dev_alloc((size_t)new_slots * ((size_t)N_ + 1) * sizeof(int32_t));
+        B200_CUDA(cudaMemset(nseg_, 0, (size_t)new_slots * seg_stride * sizeof(int32_t)));
+        B200_CUDA(cudaMemset(ncomp, 0, (size_t)new_slots * ((size_t)N_ + 1) * sizeof(int32_t)));
+        if (seg && N == N_ && nb == nb_) {
+            // same segmentation: carry the history over (slots only ever grow)
+            const size_t old_stride = (size_t)N + nseg;
             for (int back = 1; back <= slots && back < new_slots; ++back) {
                 const int64_t s = timestep - back;
                 int64_t os = s % slots, ns = s % new_slots;
                 if (os < 0) os += slots;
                 if (ns < 0) ns += new_slots;
-                B200_CUDA(cudaMemcpy(nd + ns * (size_t)stride_, dev + os * (size_t)stride,
-                                     stride * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+                B200_CUDA(cudaMemcpy(nseg_ + ns * seg_stride, seg + os * old_stride,
+                                     old_stride * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+                B200_CUDA(cudaMemcpy(ncomp + ns * ((size_t)N_ + 1), compact + os * ((size_t)N + 1),
+                                     ((size_t)N + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice));
             }
         }
-        dev_free(dev);
-        dev = nd;
-        slots = new_slots;
-        stride = stride_;
+        close_peers();
+        dev_free(seg); dev_free(compact);
+        seg = nseg_; compact = ncomp;
+        slots = new_slots; N = N_; nb = nb_; nseg = new_nseg;
+        // first neuron of every segment (same arithmetic as owned_cta on the device)
+        std::vector<int32_t> start(nseg + 1);
+        for (int q = 0; q < st.world; ++q) {
+            int64_t lo, hi;
+            rank_range_host(N, q, st.world, lo, hi);
+            for (int b = 0; b < nb; ++b)
+                start[q * nb + b] = (int32_t)warp_first_host(lo, hi, (int64_t)b * kWarps, (int64_t)nb * kWarps);
+        }
+        start[nseg] = N;
+        dev_free(seg_start);
+        seg_start = (int32_t*)dev_alloc((nseg + 1) * sizeof(int32_t));
+        B200_CUDA(cudaMemcpy(seg_start, start.data(), (nseg + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+        if (!done) {
+            done = (unsigned long long*)dev_alloc(kMaxRanks * sizeof(unsigned long long));
+            B200_CUDA(cudaMemset(done, 0, kMaxRanks * sizeof(unsigned long long)));
+        }
     }
-    int32_t* slot_ptr(int64_t timestep) const {
+
+    static void rank_range_host(int64_t N, int rank, int world, int64_t& lo, int64_t& hi) {
+        int64_t per = (N + world - 1) / world;
+        per = (per + 31) & ~(int64_t)31;
+        lo = (int64_t)rank * per; if (lo > N) lo = N;
+        hi = lo + per; if (hi > N) hi = N;
+    }
+    static int64_t warp_first_host(int64_t lo, int64_t hi, int64_t g, int64_t G) {
+        const int64_t T = (hi - lo + 31) >> 5;
+        int64_t e = lo + 32 * ((g * T) / G);
+        return e < hi ? e : hi;
+    }
+
+    // multi-GPU: map every peer's ring and `done` counters (CUDA IPC, one exchange per allocation)
+    void open_peers() {
+        RuntimeState& st = state();
+        if (st.world <= 1 || peers_open) return;
+        B200_CUDA(cudaDeviceSynchronize());
+        struct Handles { cudaIpcMemHandle_t seg, done; } mine, all[kMaxRanks];
+        B200_CUDA(cudaIpcGetMemHandle(&mine.seg, seg));
+        B200_CUDA(cudaIpcGetMemHandle(&mine.done, done));
+        host_allgather(&mine, all, sizeof(Handles));
+        for (int q = 0; q < st.world; ++q) {
+            if (q == st.rank) { peer_seg[q] = seg; peer_done[q] = done; continue; }
+            B200_CUDA(cudaIpcOpenMemHandle(&peer_seg[q], all[q].seg, cudaIpcMemLazyEnablePeerAccess));
+            B200_CUDA(cudaIpcOpenMemHandle(&peer_done[q], all[q].done, cudaIpcMemLazyEnablePeerAccess));
+        }
+        peers_open = true;
+    }
+
+    EventSpaceDev view() const {
+        RuntimeState& st = state();
+        EventSpaceDev v;
+        memset(&v, 0, sizeof(v));
+        v.seg = seg; v.compact = compact; v.seg_start = seg_start;
+        v.slots = slots; v.seg_stride = N + nseg; v.N = N; v.nseg = nseg; v.lag = lag(); v.id = id;
+        int64_t lo, hi;
+        rank_range_host(N, st.rank, st.world, lo, hi);
+        v.rank_lo = (int)lo; v.rank_hi = (int)hi;
+        v.done = done;
+        for (int q = 0; q < st.world; ++q) {
+            v.peer_seg[q] = (int32_t*)peer_seg[q];
+            v.peer_done[q] = peer_done[q] ? (unsigned long long*)peer_done[q] + st.rank : nullptr;
+        }
+        return v;
+    }
+    const int32_t* compact_slot_ptr(int64_t timestep) const {
         int64_t s = timestep % slots;
         if (s < 0) s += slots;
-        return dev + s * (size_t)stride;
+        return compact + s * ((size_t)N + 1);
     }
 };
 
@@ -214,7 +317,8 @@ public:
     int* d_syn_ids = nullptr;
     int* d_csr_target = nullptr;
     unsigned long long* d_events = nullptr;
-    EventRing* ring = nullptr;
+    EventSpace* es = nullptr;
+    size_t n_owned = 0;            // synapses stored on this rank (post neuron owned)
 
     Pathway(std::vector<int>& _sources, int _spikes_start, int _spikes_stop)
         : sources(_sources), spikes_start(_spikes_start), spikes_stop(_spikes_stop) {}
@@ -231,15 +335,26 @@ public:
     // Slot order = (delay bin asc, source asc, synapse index asc); walking the bins from the
     // largest delay to the smallest reproduces the reference's delivery order within a step
     // (entries pushed earlier sit first in a bucket, spikequeue.h:157-190).
+    // `post_is_source`: the pathway listens to the POSTsynaptic group (on_post), i.e. `srcs` are
+    // the postsynaptic ends.  On several GPUs a rank stores only the synapses whose postsynaptic
+    // neuron it owns ([post_lo, post_hi) of the postsynaptic group's parent).
     template <typename scalar>
     void prepare(int n_source, int n_target, const scalar* real_delays, size_t n_delays,
-                 const int* srcs, const int* targets, size_t n_syn, double dt, EventRing* ring_) {
+                 const int* srcs, const int* targets, size_t n_syn, double dt, EventSpace* es_,
+                 bool post_is_source, int64_t n_post_parent) {
         runtime_init();
         release();
         Nsource = n_source;
         Ntarget = n_target;
         n_synapses = n_syn;
-        ring = ring_;
+        es = es_;
+        int64_t post_lo = 0, post_hi = INT64_MAX;
+        if (state().world > 1)
+            EventSpace::rank_range_host(n_post_parent, state().rank, state().world, post_lo, post_hi);
+        const int* post_end = post_is_source ? srcs : targets;
+        auto owned = [&](size_t i) -> bool {
+            return state().world <= 1 || !post_end || (post_end[i] >= post_lo && post_end[i] < post_hi);
+        };
         if (n_syn >= (size_t)INT32_MAX)
             throw std::runtime_error("b200: more than 2^31-1 synapses in one pathway shard");
         const int nsrc = spikes_stop - spikes_start;
@@ -277,42 +392,46 @@ public:
         const size_t nrows = (size_t)nbins * (nsrc + 1);
         std::vector<int> rowptr(nrows + 1, 0);
         // row r = bin*(nsrc+1) + src ; the extra row per bin keeps rowptr[bin][nsrc] addressable
+        n_owned = 0;
         for (size_t i = 0; i < n_syn; ++i) {
             const int s = srcs[i] - spikes_start;
             if (s < 0 || s >= nsrc) throw std::runtime_error("b200: synapse source outside pathway source range");
+            if (!owned(i)) continue;
             const size_t r = (size_t)(hetero ? dsteps[i] : 0) * (nsrc + 1) + s;
             rowptr[r + 1]++;
+            n_owned++;
         }
         for (size_t r = 0; r < nrows; ++r) rowptr[r + 1] += rowptr[r];
-        std::vector<int> syn_ids(n_syn), csr_target(n_syn);
+        std::vector<int> syn_ids(n_owned), csr_target(n_owned);
         {
             std::vector<int> cursor(rowptr.begin(), rowptr.end() - 1);
             for (size_t i = 0; i < n_syn; ++i) {
+                if (!owned(i)) continue;
                 const int s = srcs[i] - spikes_start;
                 const size_t r = (size_t)(hetero ? dsteps[i] : 0) * (nsrc + 1) + s;
                 syn_ids[cursor[r]++] = (int)i;
             }
         }
-        identity = true;
-        for (size_t k = 0; k < n_syn; ++k) {
+        identity = n_owned == n_syn;
+        for (size_t k = 0; k < n_owned; ++k) {
             if (syn_ids[k] != (int)k) identity = false;
             csr_target[k] = targets ? targets[syn_ids[k]] : 0;
         }
         d_bin_delay = (int*)dev_alloc(std::max<size_t>(1, nbins) * sizeof(int));
         d_rowptr = (int*)dev_alloc((nrows + 1) * sizeof(int));
-        d_syn_ids = (int*)dev_alloc(std::max<size_t>(1, n_syn) * sizeof(int));
-        d_csr_target = (int*)dev_alloc(std::max<size_t>(1, n_syn) * sizeof(int));
+        d_syn_ids = (int*)dev_alloc(std::max<size_t>(1, n_owned) * sizeof(int));
+        d_csr_target = (int*)dev_alloc(std::max<size_t>(1, n_owned) * sizeof(int));
         if (nbins) B200_CUDA(cudaMemcpy(d_bin_delay, bin_delay.data(), nbins * sizeof(int), cudaMemcpyHostToDevice));
         B200_CUDA(cudaMemcpy(d_rowptr, rowptr.data(), (nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        if (n_syn) {
-            B200_CUDA(cudaMemcpy(d_syn_ids, syn_ids.data(), n_syn * sizeof(int), cudaMemcpyHostToDevice));
-            B200_CUDA(cudaMemcpy(d_csr_target, csr_target.data(), n_syn * sizeof(int), cudaMemcpyHostToDevice));
+        if (n_owned) {
+            B200_CUDA(cudaMemcpy(d_syn_ids, syn_ids.data(), n_owned * sizeof(int), cudaMemcpyHostToDevice));
+            B200_CUDA(cudaMemcpy(d_csr_target, csr_target.data(), n_owned * sizeof(int), cudaMemcpyHostToDevice));
         }
         if (!d_events) {
             d_events = (unsigned long long*)dev_alloc(sizeof(unsigned long long));
             B200_CUDA(cudaMemset(d_events, 0, sizeof(unsigned long long)));
         }
-        if (ring) ring->require(max_delay + 1);
+        if (es) es->require(bin_delay.empty() ? 0 : bin_delay.front(), max_delay);
         prepared = true;
     }
 
@@ -326,9 +445,7 @@ public:
         v.rowptr = d_rowptr;
         v.syn_ids = d_syn_ids;
         v.csr_target = d_csr_target;
-        v.ring = ring ? ring->dev : nullptr;
-        v.ring_slots = ring ? ring->slots : 1;
-        v.ring_stride = ring ? ring->stride : 1;
+        v.es = es ? es->id : -1;
         v.events = d_events;
         return v;
     }

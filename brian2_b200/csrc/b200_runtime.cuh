@@ -57,16 +57,30 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// system-scope flavours (multi-GPU: data and flags cross NVLink into peer memory)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Grid barrier for the persistent kernel.  Monotonic 64-bit arrival counter (never reset inside
 // a launch); `target` is thread-0 private state.  Thread 0 fences on both sides (the gpu-scope
 // fence also invalidates this SM's L1, so plain loads after the barrier see other CTAs' writes).
+// With several GPUs the arrival fence is system-scope: stores this CTA sent to peer rings are
+// then ordered before whatever CTA 0 publishes after the barrier (see publish_done).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target,
-                                             int nb) {
+                                             const Ctx& c) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += (unsigned long long)nb;
-        __threadfence();
+        target += (unsigned long long)c.nb;
+        if (c.world > 1) __threadfence_system(); else __threadfence();
         atomicAdd(counter, 1ULL);
         while (ld_acquire_u64(counter) < target) {
         }
@@ -76,65 +90,93 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
 }
 
 // ---------------------------------------------------------------------------------------------
-// Owned-slice partition
+// Partition of the elements of a group: first over ranks (contiguous blocks, multiple of 32),
+// then over the warps of the grid in units of 32-element "tasks" (contiguous per warp, so the
+// spike ids a CTA produces are ascending and the ids of CTA b precede those of CTA b+1).
+// Every per-element code object uses this one mapping, so element-private read-after-write
+// chains between code objects (stateupdate -> threshold -> reset) need no grid barrier.
 // ---------------------------------------------------------------------------------------------
 struct Slice {
     int64_t lo;   // first element of this warp's slice
-    int64_t hi;   // lo + slice length (may exceed N: guard with idx < N)
+    int64_t hi;   // one past the last element
 };
 
-__device__ __forceinline__ int64_t owned_chunk(int64_t N, int nb) {
-    int64_t per = (N + nb - 1) / nb;
-    return (per + (kBlock - 1)) & ~(int64_t)(kBlock - 1);
+__host__ __device__ __forceinline__ void rank_range(int64_t N, int rank, int world, int64_t& lo, int64_t& hi) {
+    int64_t per = (N + world - 1) / world;
+    per = (per + 31) & ~(int64_t)31;
+    lo = (int64_t)rank * per; if (lo > N) lo = N;
+    hi = lo + per; if (hi > N) hi = N;
+}
+// first element owned by global warp g (of G) inside the rank range [lo, hi)
+__host__ __device__ __forceinline__ int64_t warp_first(int64_t lo, int64_t hi, int64_t g, int64_t G) {
+    const int64_t T = (hi - lo + 31) >> 5;
+    int64_t e = lo + 32 * ((g * T) / G);
+    return e < hi ? e : hi;
 }
 
 __device__ __forceinline__ Slice owned_slice(int64_t N, const Ctx& c) {
-    const int64_t chunk = owned_chunk(N, c.nb);
-    const int64_t wchunk = chunk / kWarps;
+    int64_t lo, hi;
+    rank_range(N, c.rank, c.world, lo, hi);
+    const int64_t g = (int64_t)c.bid * kWarps + (threadIdx.x >> 5), G = (int64_t)c.nb * kWarps;
     Slice s;
-    s.lo = (int64_t)c.bid * chunk + (int64_t)(threadIdx.x >> 5) * wchunk;
-    s.hi = s.lo + wchunk;
+    s.lo = warp_first(lo, hi, g, G);
+    s.hi = warp_first(lo, hi, g + 1, G);
+    return s;
+}
+// the elements owned by the whole CTA
+__device__ __forceinline__ Slice owned_cta(int64_t N, const Ctx& c) {
+    int64_t lo, hi;
+    rank_range(N, c.rank, c.world, lo, hi);
+    const int64_t G = (int64_t)c.nb * kWarps;
+    Slice s;
+    s.lo = warp_first(lo, hi, (int64_t)c.bid * kWarps, G);
+    s.hi = warp_first(lo, hi, (int64_t)(c.bid + 1) * kWarps, G);
     return s;
 }
 
-// for (idx in my lane's elements) -- idx is guarded against N by the caller
+// for (idx in my lane's elements)
 #define B200_FOR_OWNED(IDX, N_, CTX)                                                        \
     const b200::Slice _b200_sl = b200::owned_slice((int64_t)(N_), (CTX));                    \
-    for (int64_t IDX = _b200_sl.lo + (threadIdx.x & 31);                                    \
-         IDX < _b200_sl.hi && IDX < (int64_t)(N_); IDX += 32)
+    for (int64_t IDX = _b200_sl.lo + (threadIdx.x & 31); IDX < _b200_sl.hi; IDX += 32)
+
+__device__ __forceinline__ int ring_index(int64_t timestep, int slots) {
+    int64_t s = timestep % slots;
+    if (s < 0) s += slots;
+    return (int)s;
+}
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldcg(a + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
 // ---------------------------------------------------------------------------------------------
-// Ordered compaction of owned-slice flags into an event space (ids ascending, count at [N]).
+// Thresholder output: the CTA's spikes go, ascending, into the CTA's own segment of the event
+// space -- no communication with other CTAs (the reference's loop is serial, threshold.cpp:18-31).
 //   mask   bit k of lane l  <=>  element (slice.lo + 32*k + l) fired
-//   ws     look-back workspace, one u64 per CTA: (epoch << 32) | count ; epoch must be unique
-//          per call for this workspace and never 0.
-// Called by ALL threads of ALL CTAs (CTAs without elements publish 0).
+// Called by ALL threads of ALL CTAs.  On several GPUs every store is repeated into each peer's
+// ring (NVLink P2P); the step becomes visible to the peers when CTA 0 publishes `done` after the
+// next grid barrier (publish_done).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void compact_owned(unsigned long long mask, int niter, int64_t N,
-                                              const Ctx& c, int32_t* __restrict__ eventspace,
-                                              unsigned long long* ws, unsigned int epoch) {
+__device__ __forceinline__ void publish_owned(unsigned long long mask, int niter, const Ctx& c,
+                                              const EventSpaceDev& es, int64_t timestep) {
     __shared__ int s_warp[kWarps];
-    __shared__ int s_pred[kWarps];
-    __shared__ int s_base;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const Slice sl = owned_slice(N, c);
+    const Slice sl = owned_slice(es.N, c);
+    const size_t slot_off = (size_t)ring_index(timestep, es.slots) * (size_t)es.seg_stride;
+    const int segi = c.rank * c.nb + c.bid;
 
-    // Only CTAs that own elements take part (for small groups most of the grid has nothing to
-    // compact and must not pay the look-back latency); the last owning CTA writes the count.
-    const int64_t chunk = owned_chunk(N, c.nb);
-    const int nact = (int)((N + chunk - 1) / chunk);
-    if (c.bid >= nact) return;
-
-    // 1. per-warp totals
-    int mine = __popcll(mask);
-    int wtotal = mine;
+    int wtotal = __popcll(mask);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wtotal += __shfl_xor_sync(0xffffffffu, wtotal, o);
+    __syncthreads();            // s_warp may still be read by a previous call
     if (lane == 0) s_warp[warp] = wtotal;
     __syncthreads();
-
-    // 2. CTA total -> publish ; exclusive warp offsets
     int woff = 0, ctotal = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
@@ -142,71 +184,185 @@ __device__ __forceinline__ void compact_owned(unsigned long long mask, int niter
         if (w < warp) woff += v;
         ctotal += v;
     }
-    if (threadIdx.x == 0 && c.bid + 1 < nact) {
-        st_release_u64(&ws[c.bid], ((unsigned long long)epoch << 32) | (unsigned int)ctotal);
-    }
-
-    // 3. decoupled look-back: thread j < bid polls predecessor j (nb <= kBlock)
-    int pred = 0;
-    if ((int)threadIdx.x < c.bid) {
-        unsigned long long v;
-        do {
-            v = ld_acquire_u64(&ws[threadIdx.x]);
-        } while ((unsigned int)(v >> 32) != epoch);
-        pred = (int)(unsigned int)(v & 0xffffffffu);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pred += __shfl_xor_sync(0xffffffffu, pred, o);
-    if (lane == 0) s_pred[warp] = pred;
-    __syncthreads();
+    const size_t base = slot_off + (size_t)es.seg_start[segi];
     if (threadIdx.x == 0) {
-        int b = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) b += s_pred[w];
-        s_base = b;
-        if (c.bid == nact - 1) eventspace[N] = b + ctotal;
+        es.seg[slot_off + es.N + segi] = ctotal;
+        for (int q = 0; q < c.world; ++q)
+            if (q != c.rank) es.peer_seg[q][slot_off + es.N + segi] = ctotal;
     }
-    __syncthreads();
-
-    // 4. write ids in ascending order: iteration-major, lane-minor inside the warp slice
-    int pos = s_base + woff;
     if (wtotal > 0) {
+        int pos = woff;
         for (int k = 0; k < niter; ++k) {
             const bool f = (mask >> k) & 1ULL;
             const unsigned int bal = __ballot_sync(0xffffffffu, f);
             if (f) {
                 const int p = pos + __popc(bal & ((1u << lane) - 1u));
-                eventspace[p] = (int32_t)(sl.lo + 32 * (int64_t)k + lane);
+                const int32_t id = (int32_t)(sl.lo + 32 * (int64_t)k + lane);
+                es.seg[base + p] = id;
+                for (int q = 0; q < c.world; ++q)
+                    if (q != c.rank) es.peer_seg[q][base + p] = id;
             }
             pos += __popc(bal);
         }
     }
+    __syncthreads();            // the CTA's own segment is now readable by all its threads
 }
 
-// ---------------------------------------------------------------------------------------------
-// Sorted-range helpers on an event space (ids ascending): first index with id >= x
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int x) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] < x) lo = mid + 1; else hi = mid;
+// Multi-GPU: after the grid barrier that follows the thresholder (all CTAs' peer stores are
+// fenced at system scope by then), tell every peer that step `timestep` of this rank is complete.
+__device__ __forceinline__ void publish_done(const Ctx& c, const EventSpaceDev& es, int64_t timestep) {
+    if (c.world > 1 && c.bid == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int q = 0; q < c.world; ++q)
+            if (q != c.rank) st_release_sys_u64(es.peer_done[q], (unsigned long long)(timestep + 1));
     }
-    return lo;
 }
 
+// ---------------------------------------------------------------------------------------------
+// View of one step's spike list straight from the segments: exclusive prefix sums of the
+// segment counts in shared memory (cached per CTA under a tag, so the code objects of one phase
+// build it once).  Global spike number g -> id by a binary search in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct SpikeView {
+    const int32_t* slot;    // seg + slot offset
+    const int32_t* seg_start;
+    const int* pref;        // shared: pref[j - seg_lo] = number of spikes in segments [seg_lo, j)
+    int seg_lo, nseg;       // segments covered
+    int total;
+};
 
-// spike list that a delay-bin has to deliver at `timestep`
-__device__ __forceinline__ int ring_index(int64_t timestep, int slots) {
-    int64_t s = timestep % slots;
-    if (s < 0) s += slots;
-    return (int)s;
+__device__ int* view_storage(long long** tag) {
+    __shared__ int s_pref[kMaxSegments + 1];
+    __shared__ long long s_tag;
+    *tag = &s_tag;
+    return s_pref;
 }
-__device__ __forceinline__ const int32_t* ring_slot(const int32_t* ring, int slots, int stride,
-                                                    int64_t timestep) {
-    int64_t s = timestep % slots;
-    if (s < 0) s += slots;
-    return ring + s * (int64_t)stride;
+// to be called once at kernel start
+__device__ __forceinline__ void view_reset() {
+    long long* tag;
+    view_storage(&tag);
+    if (threadIdx.x == 0) *tag = 0;
+    __syncthreads();
+}
+
+// wait until every peer has published step `timestep` of this event space (multi-GPU)
+__device__ __forceinline__ void wait_peers(const Ctx& c, const EventSpaceDev& es, int64_t timestep,
+                                           Control* ctrl) {
+    if (c.world > 1 && timestep >= 0) {
+        if (threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
+            const unsigned long long need = (unsigned long long)(timestep + 1);
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(&es.done[threadIdx.x]) < need) {
+                if (clock64() - t0 > 40000000000LL || ld_volatile_s32(&ctrl->error)) {   // ~20 s
+                    ctrl->error = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t timestep, const Ctx& c,
+                                                bool local_only, Control* ctrl) {
+    long long* tagp;
+    int* pref = view_storage(&tagp);
+    SpikeView v;
+    v.slot = es.seg + (size_t)ring_index(timestep, es.slots) * (size_t)es.seg_stride;
+    v.seg_start = es.seg_start;
+    v.pref = pref;
+    const bool local = local_only && c.world > 1;
+    v.seg_lo = local ? c.rank * c.nb : 0;
+    v.nseg = local ? c.nb : es.nseg;
+    const long long tag = ((long long)(es.id * 2 + (local ? 1 : 0) + 1) << 44) ^ (timestep + 1);
+    __syncthreads();
+    if (*tagp != tag) {
+        if (!local) wait_peers(c, es, timestep, ctrl);
+        // block-wide exclusive scan of v.nseg counts (<= kMaxSegments)
+        __shared__ int s_wsum[kWarps];
+        const int per = (v.nseg + kBlock - 1) / kBlock;
+        const int first = (int)threadIdx.x * per;
+        int vals[kMaxSegments / kBlock];
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxSegments / kBlock; ++k) {
+            const int j = first + k;
+            vals[k] = (k < per && j < v.nseg) ? __ldcg(v.slot + es.N + v.seg_lo + j) : 0;
+            mine += vals[k];
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int x = s_wsum[w];
+            if (w < warp) woff += x;
+            tot += x;
+        }
+        int run = woff + incl - mine;
+#pragma unroll
+        for (int k = 0; k < kMaxSegments / kBlock; ++k) {
+            const int j = first + k;
+            if (k < per && j < v.nseg) { pref[j] = run; run += vals[k]; }
+        }
+        if (threadIdx.x == 0) { pref[v.nseg] = tot; *tagp = tag; }
+        __syncthreads();
+    }
+    v.total = pref[v.nseg];
+    return v;
+}
+
+// id of spike number g (0 <= g < total) of the view
+__device__ __forceinline__ int32_t view_id(const SpikeView& v, int g) {
+    int lo = 0, hi = v.nseg;           // last j with pref[j] <= g
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (v.pref[mid] <= g) lo = mid; else hi = mid;
+    }
+    return __ldcg(v.slot + v.seg_start[v.seg_lo + lo] + (g - v.pref[lo]));
+}
+
+// number of spikes of the view with id < x (for monitors of subgroups, spikemonitor.cpp:15-33)
+__device__ __forceinline__ int view_count_below(const SpikeView& v, const EventSpaceDev& es, int x) {
+    if (x <= v.seg_start[v.seg_lo]) return 0;
+    if (x >= v.seg_start[v.seg_lo + v.nseg]) return v.total;
+    int lo = 0, hi = v.nseg;           // segment with seg_start[lo] <= x < seg_start[lo+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (v.seg_start[v.seg_lo + mid] <= x) lo = mid; else hi = mid;
+    }
+    const int cnt = v.pref[lo + 1] - v.pref[lo];
+    return v.pref[lo] + lower_bound_i32(v.slot + v.seg_start[v.seg_lo + lo], cnt, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compaction: the reference layout of `_spikespace` (ids ascending in [0,count), count at [N])
+// for step (timestep - lag), for the consumers that look back in time (delayed synapses) and
+// for the host mirror.  CTA b copies the segments b, b+nb, ... (one per rank).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compact_segments(const EventSpaceDev& es, int64_t timestep, const Ctx& c,
+                                                 Control* ctrl) {
+    const int64_t s = timestep - es.lag;
+    const SpikeView v = view_build(es, s, c, false, ctrl);
+    int32_t* out = es.compact + (size_t)ring_index(s, es.slots) * (size_t)(es.N + 1);
+    for (int j = c.bid; j < v.nseg; j += c.nb) {
+        const int beg = v.pref[j], cnt = v.pref[j + 1] - beg;
+        const int32_t* src = v.slot + v.seg_start[j];
+        for (int k = threadIdx.x; k < cnt; k += kBlock) out[beg + k] = __ldcg(src + k);
+    }
+    if (c.bid == 0 && threadIdx.x == 0) out[es.N] = v.total;
+}
+
+// compact spike list of step `timestep` (valid once compact_segments ran for it)
+__device__ __forceinline__ const int32_t* compact_slot(const EventSpaceDev& es, int64_t timestep) {
+    return es.compact + (size_t)ring_index(timestep, es.slots) * (size_t)(es.N + 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,36 @@ struct Clk {
 struct Ctx {
     int bid;
     int nb;
+    int rank;
+    int world;
+};
+
+constexpr int kMaxRanks = 8;           // GPUs of one box that can share a network
+constexpr int kMaxSegments = kMaxRanks * kBlock;   // spike-list segments of one event space
+
+// Device view of one event space ("spike ring").  A step's spike list exists in two forms:
+//   * segments: CTA b of rank r writes the ids of ITS neurons that fired (ascending) at
+//     seg[slot][seg_start[r*nb+b] ...] and their number at seg[slot][N + r*nb + b]; the
+//     concatenation in segment order is the ascending `_spikespace` of the reference
+//     (threshold.cpp:24-31).  Produced without any inter-CTA communication; on several GPUs the
+//     same stores also go to every peer's ring over NVLink.
+//   * compact: ids [0, count) + count at [N], the reference layout, built `lag` steps later by
+//     `compact_segments` for the consumers that look back in time (synaptic delays).
+struct EventSpaceDev {
+    int32_t* seg;             // [slots][seg_stride]
+    int32_t* compact;         // [slots][N + 1]
+    const int32_t* seg_start; // [nseg + 1] first neuron of every segment (absolute id)
+    int slots;
+    int seg_stride;           // N + nseg
+    int N;
+    int nseg;                 // world * nb
+    int lag;                  // compaction of step s happens during step s + lag
+    int id;                   // index of this event space (tag of the cached view)
+    int rank_lo, rank_hi;     // neurons owned by this rank
+    // multi-GPU: peers' rings and the per-rank "steps published" counters (this rank's copy)
+    int32_t* peer_seg[kMaxRanks];
+    unsigned long long* peer_done[kMaxRanks];   // address of done[my_rank] on every peer
+    unsigned long long* done;                   // [kMaxRanks] local: done[q] = steps published by rank q
 };
 
 // Device view of a synaptic pathway (built by b200_host.h: Pathway::prepare)
@@ -32,9 +62,7 @@ struct PathwayDev {
     const int* rowptr;        // [nbins*(nsrc+1)+1] slot offsets
     const int* syn_ids;       // [S] synapse index per slot (sorted by delay, source, index)
     const int* csr_target;    // [S] the non-source end of the synapse, packed in slot order
-    const int32_t* ring;      // spike ring of the source event space
-    int ring_slots;
-    int ring_stride;          // N_group + 1
+    int es;                   // (unused on the device; kept for debugging)
     unsigned long long* events;   // number of delivered synaptic events (for the metric)
 };
 
@@ -44,7 +72,7 @@ struct Control {
     int stop;                       // != 0: leave the step loop after the current step
     int steps_done;                 // steps completed by the last launch
     int overflow;                   // a monitor buffer is (nearly) full: host must grow it
-    int pad;
+    int error;                      // != 0: device-side failure (1: peer wait timed out)
 };
 
 }  // namespace b200

@@ -277,6 +277,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
         kwds["b200_scalar_members"] = scal_members
         kwds["b200_serial"] = serial
         # remembered by the device for the barrier analysis of the persistent kernel
+        access["serial"] = serial
         self.device._b200_access[self.name] = access
         return sc_code, ve_code, kwds
 
@@ -291,11 +292,12 @@ class CUDACodeGenerator(CPPCodeGenerator):
         if field is not None:
             return f"const {ctype}* {pointer_name} = &_clks.{var.owner.name}.{field};"
         if is_eventspace(var):
+            # generic access = the compacted list of the current step (reference layout); the
+            # device templates themselves read the segments through b200::view_* instead
             clk = var.owner.clock.name
             return (
-                f"{ctype}* {pointer_name} = _A._ring{array_name} + "
-                f"(size_t)b200::ring_index(_clks.{clk}.timestep, _A._ringslots{array_name})"
-                f" * (size_t){var.size};"
+                f"const {ctype}* {pointer_name} = b200::compact_slot(_A._es{array_name}, "
+                f"_clks.{clk}.timestep);"
             )
         return f"{ctype}* {self.restrict}{pointer_name} = _A.{array_name};"
 

@@ -166,6 +166,16 @@ class B200Device(CPPStandaloneDevice):
                 f"{owner.name}.{template_name}.{name.rstrip('*')}".encode()
             )
             template_kwds["b200_template_name"] = template_name
+            if template_name == "synapses_push_spikes":
+                # size of the group the postsynaptic indices refer to (partition by post neuron)
+                post_group = owner.synapses.target
+                post_parent = getattr(post_group, "source", post_group)
+                template_kwds["b200_post_parent_size"] = int(len(post_parent))
+            if template_name == "statemonitor":
+                from brian2.groups.neurongroup import NeuronGroup
+
+                src = owner.source
+                template_kwds["b200_source_size"] = int(len(src)) if isinstance(src, NeuronGroup) else None
         codeobj = super().code_object(
             owner,
             name,
@@ -247,10 +257,54 @@ class B200Device(CPPStandaloneDevice):
 
         clocks_by_name = {clock.name: clock for clock in self.clocks}
         entries = []
-        for line in run_lines:
+        compactions = []     # implicit companion of every thresholder: compaction of its event space
+        last_add = -1
+        for i, line in enumerate(run_lines):
             m = _re.match(rf"\s*{_re.escape(net.name)}\.add\(&(\w+), _run_(\w+)\);", line)
             if m and m.group(2) in self.code_objects:
-                entries.append((clocks_by_name[m.group(1)], self.code_objects[m.group(2)]))
+                last_add = i
+                codeobj = self.code_objects[m.group(2)]
+                clock = clocks_by_name[m.group(1)]
+                entries.append((clock, codeobj))
+                info = self._b200_info.get(codeobj.name)
+                if info is not None and info["template"] == "threshold":
+                    es = info["template_kwds"]["eventspace_variable"]
+                    compactions.append((clock, self.get_array_name(es, access_data=False)))
+        # Only order-dependent (serial) synaptic code reads the compacted list of the CURRENT
+        # step; everything else reads the segments or older steps, so the compaction normally
+        # goes to the end of the step where it costs no extra barrier.
+        def needs_early(es_name):
+            for _, co in entries:
+                if isinstance(co, tuple):
+                    continue
+                info = self._b200_info.get(co.name)
+                if info is None or info["template"] != "synapses":
+                    continue
+                pathway = info["template_kwds"]["pathway"]
+                src_es = pathway.source.variables[pathway.eventspace_name]
+                if (self.get_array_name(src_es, access_data=False) == es_name
+                        and self._b200_access.get(co.name, {}).get("serial")):
+                    return True
+            return False
+
+        extra_lines = []
+        for clock, es_name in compactions:
+            item = (clock, ("compact", es_name, clock.name))
+            line = f"{net.name}.add(&{clock.name}, _run_b200_compact{es_name});"
+            if needs_early(es_name):
+                pos = next(k for k, (_, co) in enumerate(entries)
+                           if not isinstance(co, tuple) and self._b200_info.get(co.name, {}).get("template") == "threshold"
+                           and self.get_array_name(self._b200_info[co.name]["template_kwds"]["eventspace_variable"],
+                                                   access_data=False) == es_name)
+                entries.insert(pos + 1, item)
+                # same position in the generated net.add sequence
+                k = [j for j, l in enumerate(run_lines) if f"_run_{entries[pos][1].name});" in l][0]
+                run_lines.insert(k + 1, line)
+                last_add += 1
+            else:
+                entries.append(item)
+                extra_lines.append(line)
+        run_lines[last_add + 1:last_add + 1] = extra_lines
         plan_index = len(self._b200_plans)
         self._b200_plans.append(entries)
         run_call = f"{net.name}.run("
@@ -278,7 +332,10 @@ class B200Device(CPPStandaloneDevice):
         )
         template = info["template"]
         kw = info["template_kwds"]
-        owned = template in ("stateupdate", "threshold")
+        # "owned": every element is touched only by the CTA that owns it in the common partition
+        owned = template in ("stateupdate", "threshold", "reset") or (
+            template == "statemonitor" and kw.get("b200_source_size") is not None
+        )
         priv_r = set(acc["read"]) if owned else set()
         priv_w = set(acc["write"]) if owned else set()
         shared_r = set(acc["scattered_read"]) | (set() if owned else set(acc["read"]))
@@ -290,14 +347,21 @@ class B200Device(CPPStandaloneDevice):
             if varname in codeobj.variables and isinstance(codeobj.variables[varname], ArrayVariable):
                 shared_w.add(name_of(codeobj.variables[varname]))
         if template == "threshold":
+            # the CTA's own segment of the event space: other CTAs read it -> shared write
             shared_w.add(name_of(es))
             if kw.get("_uses_refractory"):
                 priv_w.add(name_of(codeobj.variables["not_refractory"]))
                 priv_w.add(name_of(codeobj.variables["lastspike"]))
-        elif template in ("reset", "spikemonitor", "synapses"):
-            if es is None and template == "synapses":
-                es = kw["pathway"].variables[kw["pathway"].eventspace_name]
+        elif template == "reset":
+            pass   # reads the CTA's own segment only (written by the same CTA's thresholder)
+        elif template == "spikemonitor":
             shared_r.add(name_of(es))
+        elif template == "synapses":
+            if es is None:
+                es = kw["pathway"].source.variables[kw["pathway"].eventspace_name]
+            shared_r.add(name_of(es))
+            if acc.get("serial"):
+                shared_r.add(name_of(es) + "__compact")
         elif template == "ratemonitor":
             shared_r.add(name_of(codeobj.variables["_spikespace"]))
         if template in ("spikemonitor", "statemonitor", "ratemonitor"):
@@ -316,7 +380,35 @@ class B200Device(CPPStandaloneDevice):
         same owned partition) with something executed since the previous barrier."""
         items = []
         ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
+        ph_thresholders = []   # event spaces written since the last barrier (multi-GPU publish)
+
+        def add(name, kind, pr, pw, sr, sw, extra=None):
+            nonlocal ph_pr, ph_pw, ph_sr, ph_sw, ph_thresholders
+            conflict = bool(
+                (sw | pw) & (ph_sr | ph_sw)      # I write what somebody read/wrote (shared)
+                or sw & (ph_pr | ph_pw)           # shared write vs private access
+                or (sr | pr) & ph_sw              # I read what somebody wrote (shared)
+                or sr & ph_pw                     # shared read of a privately written array
+            )
+            item = {"name": name, "kind": kind, "barrier": conflict and len(items) > 0, "publish": []}
+            if conflict:
+                item["publish"] = list(ph_thresholders)
+                ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
+                ph_thresholders = []
+            if extra:
+                item.update(extra)
+            items.append(item)
+            ph_pr |= pr
+            ph_pw |= pw
+            ph_sr |= sr
+            ph_sw |= sw
+
         for clock, codeobj in entries:
+            if isinstance(codeobj, tuple):   # ("compact", event space array name, clock name)
+                _, es_name, clk = codeobj
+                add(f"compact{es_name}", "compact", set(), set(), {es_name}, {es_name + "__compact"},
+                    {"es": es_name, "clock": clk})
+                continue
             if not self.is_device_codeobj(codeobj):
                 raise NotImplementedError(
                     f"Code object '{codeobj.name}' cannot run inside the simulation loop on the b200 device"
@@ -325,19 +417,14 @@ class B200Device(CPPStandaloneDevice):
             if info["template"] == "synapses_push_spikes":
                 continue
             pr, pw, sr, sw = self._codeobj_access(codeobj)
-            conflict = bool(
-                (sw | pw) & (ph_sr | ph_sw)      # I write what somebody read/wrote (shared)
-                or sw & (ph_pr | ph_pw)           # shared write vs private access
-                or (sr | pr) & ph_sw              # I read what somebody wrote (shared)
-                or sr & ph_pw                     # shared read of a privately written array
-            )
-            if conflict:
-                ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
-            items.append({"name": codeobj.name, "barrier": conflict and len(items) > 0})
-            ph_pr |= pr
-            ph_pw |= pw
-            ph_sr |= sr
-            ph_sw |= sw
+            add(codeobj.name, "codeobj", pr, pw, sr, sw)
+            if info["template"] == "threshold":
+                es = info["template_kwds"]["eventspace_variable"]
+                ph_thresholders.append(
+                    {"es": self.get_array_name(es, access_data=False), "clock": es.owner.clock.name}
+                )
+        # event spaces still unpublished at the end of the step go out with the end-of-step barrier
+        self._b200_tail_publish = list(ph_thresholders)
         return items
 
     # ------------------------------------------------------------------------------------------
@@ -613,7 +700,8 @@ class B200Device(CPPStandaloneDevice):
         plans = []
         for index, entries in enumerate(self._b200_plans):
             clocks = {clock for clock, _ in entries}
-            plan = {"index": index, "entries": [], "clock": None, "signature": "", "n_barriers": 0}
+            plan = {"index": index, "entries": [], "clock": None, "signature": "", "n_barriers": 0,
+                    "tail_publish": []}
             if len(clocks) == 1 and prefs.devices.b200.persistent and not self.enable_profiling_any:
                 clock = next(iter(clocks))
                 try:
@@ -621,6 +709,7 @@ class B200Device(CPPStandaloneDevice):
                     for it in items:
                         it["name"] = alias_of.get(it["name"], it["name"])
                     plan["entries"] = items
+                    plan["tail_publish"] = list(self._b200_tail_publish)
                     plan["clock"] = clock.name
                     plan["signature"] = " ".join(
                         ("| " if it["barrier"] else "") + it["name"] for it in items
@@ -643,6 +732,7 @@ class B200Device(CPPStandaloneDevice):
             None,
             device_code_objects=device_objs,
             code_object_aliases=sorted(alias_of.items()),
+            b200_eventspaces=self._eventspaces(),
             plans=[p for p in plans],
             user_headers=user_headers,
             profiled=bool(self.enable_profiling_any),

@@ -52,19 +52,60 @@ void _b200_launch_end(const char* name)
     }
 }
 
-// co-resident grid for a kernel: the thresholder's look-back and the grid barrier both need
-// every CTA to be resident, and the look-back polls with one thread per predecessor CTA
-static int _b200_grid_for(const void* kernel)
+// One grid size for every kernel of the project: the thresholder's segments, the element
+// partition shared by all per-element code objects and the grid barrier all assume the same
+// number of co-resident CTAs.  = min over all kernels of (occupancy-limited CTAs per SM) x SMs.
+static std::vector<const void*>& _b200_all_kernels()
 {
-    int occ = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, b200::kBlock, 0));
-    if (occ < 1) throw std::runtime_error("b200: kernel cannot be resident (registers/shared memory)");
-    int grid = std::min(occ, _b200_ctas_per_sm) * b200::state().num_sms;
-    if (_b200_grid_override > 0) grid = std::min(grid, _b200_grid_override);
-    return std::max(1, std::min(grid, b200::kBlock));
+    static std::vector<const void*> k;
+    return k;
 }
-#define B200_GRID(kernel) ([]() { static int g = 0; static int ov = -1; \
-    if (!g || ov != _b200_grid_override) { ov = _b200_grid_override; g = _b200_grid_for((const void*)kernel); } return g; }())
+struct _B200KernelRegistrar { _B200KernelRegistrar(const void* f) { _b200_all_kernels().push_back(f); } };
+#define B200_REGISTER_KERNEL(f) static _B200KernelRegistrar _b200_reg_##f((const void*)f);
+
+int _b200_grid_size()
+{
+    static int grid = 0, ov = -1, cps = -1;
+    if (grid && ov == _b200_grid_override && cps == _b200_ctas_per_sm) return grid;
+    b200::runtime_init();
+    ov = _b200_grid_override; cps = _b200_ctas_per_sm;
+    int per_sm = _b200_ctas_per_sm;
+    for (size_t i = 0; i < _b200_all_kernels().size(); i++) {
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, _b200_all_kernels()[i], b200::kBlock, 0));
+        if (occ < 1) throw std::runtime_error("b200: kernel cannot be resident (registers/shared memory)");
+        per_sm = std::min(per_sm, occ);
+    }
+    grid = per_sm * b200::state().num_sms;
+    if (_b200_grid_override > 0) grid = std::min(grid, _b200_grid_override);
+    grid = std::max(1, std::min(grid, b200::kBlock));
+    return grid;
+}
+
+// ---- implicit companions of the thresholders: compaction of an event space (stepwise mode) ----
+{% for es in b200_eventspaces %}
+__global__ void __launch_bounds__(b200::kBlock)
+_kernel_b200_compact{{es.name}}(const _B200Clocks _clks)
+{
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    b200::view_reset();
+    b200::compact_segments(_A._es{{es.name}}, _clks.{{es.clock}}.timestep, _ctx, _A._ctrl);
+}
+B200_REGISTER_KERNEL(_kernel_b200_compact{{es.name}})
+__global__ void _kernel_b200_publish{{es.name}}(const _B200Clocks _clks)
+{
+    const b200::Ctx _ctx{0, 1, _A._rank, _A._world};
+    b200::publish_done(_ctx, _A._es{{es.name}}, _clks.{{es.clock}}.timestep);
+}
+void _run_b200_compact{{es.name}}()
+{
+    if (b200::state().world > 1)   // the thresholder kernel has completed (stream order)
+        _kernel_b200_publish{{es.name}}<<<1, 32, 0, b200::state().stream>>>(_b200_clocks_now());
+    _b200_launch_begin("b200_compact{{es.name}}");
+    _kernel_b200_compact{{es.name}}<<<_b200_grid_size(), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now());
+    _b200_launch_end("b200_compact{{es.name}}");
+}
+{% endfor %}
 
 {% for codeobj in device_code_objects %}
 #include "code_objects/{{codeobj.name}}.cuh"
@@ -84,7 +125,7 @@ const B200Plan _b200_plan_{{plan.index}} = { _b200_run_chunk_{{plan.alias}}, "{{
 //   grid barriers per step: {{plan.n_barriers}} (incl. the end-of-step barrier)
 // =============================================================================================
 struct _B200Scal_{{plan.index}} {
-    {% for item in plan.entries %}
+    {% for item in plan.entries if item.kind == 'codeobj' %}
     _co_{{item.name}}::Scal {{item.name}};
     {% endfor %}
     int _unused;
@@ -93,23 +134,36 @@ struct _B200Scal_{{plan.index}} {
 __global__ void __launch_bounds__(b200::kBlock)
 _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
 {
-    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x};
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     unsigned long long _bar_target = 0ULL;
     __shared__ int _s_stop;
     _B200Clocks _clks = _clks0;
     long long _step = 0;
+    b200::view_reset();
     while (_step < _nsteps)
     {
         if (_ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
             _A._ctrl->stop = 1;
         {% for item in plan.entries %}
         {% if item.barrier %}
-        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx.nb);
-        {% endif %}
-        _dev_{{item.name}}(_ctx, _clks, _sc.{{item.name}});
+        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        {% for pub in item.publish %}
+        b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
         {% endfor %}
-        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx.nb);
-        if (threadIdx.x == 0) _s_stop = b200::ld_volatile_s32(&_A._ctrl->stop);
+        {% elif not loop.first %}
+        __syncthreads();
+        {% endif %}
+        {% if item.kind == 'compact' %}
+        b200::compact_segments(_A._es{{item.es}}, _clks.{{item.clock}}.timestep, _ctx, _A._ctrl);
+        {% else %}
+        _dev_{{item.name}}(_ctx, _clks, _sc.{{item.name}});
+        {% endif %}
+        {% endfor %}
+        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        {% for pub in plan.tail_publish %}
+        b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
+        {% endfor %}
+        if (threadIdx.x == 0) _s_stop = b200::ld_volatile_s32(&_A._ctrl->stop) | b200::ld_volatile_s32(&_A._ctrl->error);
         __syncthreads();
         const int _stop = _s_stop;
         // Clock::tick (brianlib/clocks.h:34-38)
@@ -121,12 +175,13 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     }
     if (_ctx.bid == 0 && threadIdx.x == 0) _A._ctrl->steps_done = (int)_step;
 }
+B200_REGISTER_KERNEL(_b200_persistent_{{plan.index}})
 
 static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
 {
     b200::RuntimeState& st = b200::state();
     _B200Scal_{{plan.index}} sc;
-    {% for item in plan.entries %}
+    {% for item in plan.entries if item.kind == 'codeobj' %}
     _hostscal_{{item.name}}(sc.{{item.name}});
     {% endfor %}
     sc._unused = 0;
@@ -134,12 +189,14 @@ static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
     B200_CUDA(cudaMemsetAsync(st.control, 0, sizeof(b200::Control), st.stream));
     _B200Clocks clks = _b200_clocks_now();
     void* args[] = {(void*)&clks, (void*)&nsteps, (void*)&sc};
-    const int grid = B200_GRID(_b200_persistent_{{plan.index}});
+    const int grid = _b200_grid_size();
     _b200_launch_begin("persistent_{{plan.index}}");
     B200_CUDA(cudaLaunchCooperativeKernel((const void*)_b200_persistent_{{plan.index}}, dim3(grid), dim3(b200::kBlock), args, 0, st.stream));
     _b200_launch_end("persistent_{{plan.index}}");
     B200_CUDA(cudaMemcpyAsync(st.control_host, st.control, sizeof(b200::Control), cudaMemcpyDeviceToHost, st.stream));
     B200_CUDA(cudaStreamSynchronize(st.stream));
+    if (st.control_host->error)
+        throw std::runtime_error("b200: a peer GPU did not deliver its spikes in time (multi-GPU run aborted)");
     return (long long)st.control_host->steps_done;
 }
 const B200Plan _b200_plan_{{plan.index}} = { _b200_run_chunk_{{plan.index}}, "{{plan.signature}}" };

@@ -26,10 +26,9 @@ struct _B200Arrays {
     size_t _cap{{a.name}};
     {% endif %}
     {% endfor %}
+    int _rank, _world;
     {% for es in b200_eventspaces %}
-    int32_t* _ring{{es.name}};
-    int _ringslots{{es.name}};
-    unsigned long long* _scanws{{es.name}};
+    b200::EventSpaceDev _es{{es.name}};
     {% endfor %}
     {% for pw in b200_pathways %}
     b200::PathwayDev _pw_{{pw.name}};
@@ -41,7 +40,7 @@ struct _B200Arrays {
 
 extern _B200Arrays _A_host;
 {% for es in b200_eventspaces %}
-extern b200::EventRing _b200_ring{{es.name}};
+extern b200::EventSpace _b200_es{{es.name}};
 {% endfor %}
 namespace brian {
 {% for pw in b200_pathways %}
@@ -49,9 +48,13 @@ extern b200::Pathway {{pw.name}};
 {% endfor %}
 }
 
+{% for es in b200_eventspaces %}
+void _run_b200_compact{{es.name}}();   // implicit companion of the thresholder (stepwise mode)
+{% endfor %}
 void _b200_upload();
 void _b200_download();
 void _b200_sync_constants();                 // defined next to the kernels (owns __constant__ _A)
+int _b200_grid_size();                       // CTAs of every kernel of this project (co-resident)
 _B200Clocks _b200_clocks_now();
 void _b200_prepare_steps(long long steps, bool exact);   // make monitor buffers large enough
 void _b200_launch_begin(const char* name);
@@ -74,7 +77,7 @@ int _b200_array_copy_in(const char* name, const void* data, size_t nbytes);
 
 _B200Arrays _A_host;
 {% for es in b200_eventspaces %}
-b200::EventRing _b200_ring{{es.name}};
+b200::EventSpace _b200_es{{es.name}};
 {% endfor %}
 namespace brian {
 {% for pw in b200_pathways %}
@@ -145,13 +148,17 @@ void _b200_upload()
     {% endif %}
     {% endif %}
     {% endfor %}
-    // spike rings (history survives between runs)
+    // event spaces (history survives between runs); on several GPUs the rings are mapped into
+    // every peer once per allocation (CUDA IPC handles travel through the allgather callback)
+    _A_host._rank = st.rank;
+    _A_host._world = st.world;
     {% for es in b200_eventspaces %}
-    _b200_ring{{es.name}}.ensure({{es.size}}, _now.{{es.clock}}.timestep);
-    _A_host._ring{{es.name}} = _b200_ring{{es.name}}.dev;
-    _A_host._ringslots{{es.name}} = _b200_ring{{es.name}}.slots;
-    _A_host._scanws{{es.name}} = _b200_ring{{es.name}}.scan_ws;
-    B200_CUDA(cudaMemset(_b200_ring{{es.name}}.scan_ws, 0, b200::kBlock * sizeof(unsigned long long)));
+    _b200_es{{es.name}}.id = {{loop.index}};
+    _b200_es{{es.name}}.ensure({{es.size - 1}}, _b200_grid_size(), _now.{{es.clock}}.timestep);
+    {% endfor %}
+    {% for es in b200_eventspaces %}
+    _b200_es{{es.name}}.open_peers();
+    _A_host._es{{es.name}} = _b200_es{{es.name}}.view();
     {% endfor %}
     {% for pw in b200_pathways %}
     if (brian::{{pw.name}}.prepared)
@@ -251,8 +258,8 @@ void _b200_download()
     {% if a.eventspace %}
     {
         // host mirror of an event space = the list of the last executed step
-        const long long _last = _b200_clocks_now().{{a.clock}}.timestep - 1;
-        b200::download_array(brian::{{a.name}}, _b200_ring{{a.name}}.slot_ptr(_last), {{a.size}});
+        const long long _last = _b200_clocks_now().{{a.clock}}.timestep - 1 - _b200_es{{a.name}}.lag();
+        b200::download_array(brian::{{a.name}}, _b200_es{{a.name}}.compact_slot_ptr(_last), {{a.size}});
     }
     {% elif a.kind == 'static' %}
     b200::download_array(brian::{{a.name}}, _A_host.{{a.name}}, {{a.size}});

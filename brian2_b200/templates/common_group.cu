@@ -48,9 +48,12 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}(const b200::Ctx& _ctx, con
 __global__ void __launch_bounds__(b200::kBlock)
 _kernel_{{codeobj_name}}(const _B200Clocks _clks, const _co_{{codeobj_name}}::Scal _sc)
 {
-    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x};
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    b200::view_reset();
     _dev_{{codeobj_name}}(_ctx, _clks, _sc);
 }
+
+B200_REGISTER_KERNEL(_kernel_{{codeobj_name}})
 
 void _run_{{codeobj_name}}()
 {
@@ -59,7 +62,9 @@ void _run_{{codeobj_name}}()
     {% block host_prelaunch %}
     {% endblock %}
     _b200_launch_begin("{{codeobj_name}}");
-    _kernel_{{codeobj_name}}<<<B200_GRID(_kernel_{{codeobj_name}}), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now(), _sc);
+    _kernel_{{codeobj_name}}<<<_b200_grid_size(), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now(), _sc);
+    {% block host_postlaunch %}
+    {% endblock %}
     _b200_launch_end("{{codeobj_name}}");
 }
 {% block extra_device_code %}

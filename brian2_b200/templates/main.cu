@@ -118,6 +118,19 @@ double b200_last_run_time() { return Network::_last_run_time; }
 double b200_last_run_completed_fraction() { return Network::_last_run_completed_fraction; }
 void b200_request_stop() { if (b200::state().stop_request) *b200::state().stop_request = 1; Network::_globally_stopped = true; }
 
+int b200_set_comm(int rank, int world, b200_allgather_fn allgather)
+{
+    if (world < 1 || world > b200::kMaxRanks || rank < 0 || rank >= world) return 1;
+    if (world > 1 && !allgather) return 1;
+    if (b200::state().initialised) return 2;   // must be called before the first run
+    b200::state().rank = rank;
+    b200::state().world = world;
+    b200::state().allgather = allgather;
+    return 0;
+}
+int b200_comm_rank() { return b200::state().rank; }
+int b200_comm_world() { return b200::state().world; }
+
 int b200_set_option(const char* key, double value)
 {
     const std::string k(key);
@@ -144,6 +157,7 @@ double b200_get_counter(const char* key)
     if (k == "download_seconds") return st.download_seconds;
     if (k == "device_bytes") return (double)st.bytes_allocated;
     if (k == "num_sms") return (double)st.num_sms;
+    if (k == "grid") return st.initialised ? (double)_b200_grid_size() : 0.0;
     if (k == "runs") return (double)Network::_b200_run_log.size();
     // per-run records: "run<i>.<field>"
     if (k.compare(0, 3, "run") == 0) {

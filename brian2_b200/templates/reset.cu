@@ -1,14 +1,16 @@
 {# USES_VARIABLES { N } #}
-{# Resetter: brian2/devices/cpp_standalone/templates/reset.cpp:3-23 -- scatter over this step's
-   spike list (grid-stride; one spike per thread). #}
+{# Resetter: brian2/devices/cpp_standalone/templates/reset.cpp:3-23.  Every CTA resets the
+   neurons of ITS OWN segment of this step's spike list (the ones its thresholder just found),
+   so the reset is element-private like the state update: no grid barrier is needed for it. #}
 {% extends 'common_group.cu' %}
 {% block maincode %}
-    {% set _eventspace = get_array_name(eventspace_variable) %}
-    const int32_t* _events = {{_eventspace}};
-    const int32_t _num_events = {{_eventspace}}[N];
+    const b200::EventSpaceDev& _es = _A._es{{get_array_name(eventspace_variable, access_data=False)}};
+    const int32_t* _slot = _es.seg + (size_t)b200::ring_index(_clks.{{b200_clock}}.timestep, _es.slots) * (size_t)_es.seg_stride;
+    const int _segi = _ctx.rank * _ctx.nb + _ctx.bid;
+    const int32_t _num_events = _slot[_es.N + _segi];
+    const int32_t* _events = _slot + _es.seg_start[_segi];
     {{scalar_code|autoindent}}
-    for (int32_t _index_events = _ctx.bid * b200::kBlock + threadIdx.x; _index_events < _num_events;
-         _index_events += _ctx.nb * b200::kBlock)
+    for (int32_t _index_events = threadIdx.x; _index_events < _num_events; _index_events += b200::kBlock)
     {
         const int _idx = _events[_index_events];
         const int _vectorisation_idx = _idx;

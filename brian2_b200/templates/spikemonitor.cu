@@ -2,17 +2,23 @@
 {# WRITES_TO_READ_ONLY_VARIABLES { N, count } #}
 {# Spike/event monitor: brian2/devices/cpp_standalone/templates/spikemonitor.cpp:6-51.
    The recorded ids are a contiguous run of the (ascending) spike list, so every spike's output
-   position is known without atomics: base + (j - first).  The running total N is double
-   buffered by step parity so that all CTAs can read it while one thread publishes the new
-   value.  Storage is a device append buffer; the host grows it between launches when the
-   kernel reports that fewer than one step's worst case of free slots are left. #}
+   position is known without atomics: N_old + (g - first).  The list is read straight from the
+   thresholder's segments (b200::view_*); a binary search is only needed when the monitor
+   watches a subgroup.  The running total N is double buffered by step parity so that all CTAs
+   can read it while one thread publishes the new value.  Storage is a device append buffer;
+   the host grows it between launches when the kernel reports that fewer than one step's worst
+   case of free slots are left.  On several GPUs every rank records the spikes of its own
+   neurons; the host merges the per-rank records by (t, i) after the run. #}
 {% extends 'common_group.cu' %}
 {% block maincode %}
-    {% set _eventspace = get_array_name(eventspace_variable) %}
-    const int32_t* _events = {{_eventspace}};
-    const int _num_events_all = _events[_num{{eventspace_variable.name}} - 1];
-    const int _start_idx = b200::lower_bound_i32(_events, _num_events_all, (int)_source_start);
-    const int _end_idx = b200::lower_bound_i32(_events, _num_events_all, (int)_source_stop);
+    const b200::EventSpaceDev& _es = _A._es{{get_array_name(eventspace_variable, access_data=False)}};
+    const b200::SpikeView _view = b200::view_build(_es, _clks.{{b200_clock}}.timestep, _ctx, true, _A._ctrl);
+    int _start_idx = 0, _end_idx = _view.total;
+    if ((int)_source_start > 0 || (int)_source_stop < _es.N)
+    {
+        _start_idx = b200::view_count_below(_view, _es, (int)_source_start);
+        _end_idx = b200::view_count_below(_view, _es, (int)_source_stop);
+    }
     const int _num_events = _end_idx - _start_idx;
     const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
     long long* _monN = _A._monN_{{owner.name}};
@@ -24,7 +30,7 @@
         for (int _j = _start_idx + _ctx.bid * b200::kBlock + threadIdx.x; _j < _end_idx;
              _j += _ctx.nb * b200::kBlock)
         {
-            const int _idx = _events[_j];
+            const int _idx = b200::view_id(_view, _j);
             const int _vectorisation_idx = _idx;
             {{vector_code|autoindent}}
             const long long _out = _N_old + (_j - _start_idx);

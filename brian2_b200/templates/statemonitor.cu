@@ -2,7 +2,10 @@
 {# WRITES_TO_READ_ONLY_VARIABLES { t, N } #}
 {# State monitor: brian2/devices/cpp_standalone/templates/statemonitor.cpp:5-42.  One row of
    the row-major (steps x n_rec) device buffer per call; the host sizes the buffer for the
-   whole launch beforehand, so there is no resize in the loop. #}
+   whole launch beforehand, so there is no resize in the loop.  A recorded element is read by
+   the CTA that owns it in the state updater's partition (element-private access: no grid
+   barrier against the state update that follows); on several GPUs a rank fills the columns of
+   the neurons it owns and the host merges the columns after the run. #}
 {% extends 'common_group.cu' %}
 {% block maincode %}
     const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
@@ -16,10 +19,11 @@
     }
     // scalar code
     {{scalar_code|autoindent}}
-    for (int _i = _ctx.bid * b200::kBlock + threadIdx.x; _i < (int)_num_indices;
-         _i += _ctx.nb * b200::kBlock)
+    const b200::Slice _mine = b200::owned_cta((int64_t){{b200_source_size}}, _ctx);
+    for (int _i = threadIdx.x; _i < (int)_num_indices; _i += b200::kBlock)
     {
         const int _idx = {{_indices}}[_i];
+        if (_idx < _mine.lo || _idx >= _mine.hi) continue;
         const int _vectorisation_idx = _idx;
         {{vector_code|autoindent}}
         {% for varname, var in _recorded_variables | dictsort %}

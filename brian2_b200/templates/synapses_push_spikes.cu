@@ -26,5 +26,6 @@ void _run_{{codeobj_name}}() {}
                            _b200_srcs.empty() ? 0 : &_b200_srcs[0],
                            _b200_tgts.empty() ? 0 : &_b200_tgts[0],
                            n_synapses, {{_source_dt}},
-                           &_b200_ring{{get_array_name(eventspace_variable, access_data=False)}});
+                           &_b200_es{{get_array_name(eventspace_variable, access_data=False)}},
+                           {{'true' if owner.prepost == 'post' else 'false'}}, (int64_t){{b200_post_parent_size}});
 {% endblock %}

@@ -54,6 +54,19 @@ double b200_last_run_completed_fraction(void);
 /* Ask a running simulation to stop after the current step (callable from another thread). */
 void b200_request_stop(void);
 
+/* Multi-GPU (one process per GPU of one box).  Must be called before b200_run_main.  The
+ * network is partitioned by postsynaptic neuron: rank r owns a contiguous block of every group
+ * (its state, thresholding, reset, monitors) and every synapse whose postsynaptic neuron lies
+ * in the block.  Inside the step loop the ranks exchange their spike lists by direct NVLink
+ * stores into each other's spike rings (CUDA IPC mapped peer memory) -- no host involvement.
+ * `allgather` is only used outside the loop (IPC handle exchange, end-of-run barrier): it must
+ * gather `nbytes_per_rank` bytes from every rank into `recv` (rank order) and return 0.
+ * Reference counterpart: none (brian2 has no multi-process mode). */
+typedef int (*b200_allgather_fn)(const void* send, void* recv, size_t nbytes_per_rank);
+int b200_set_comm(int rank, int world, b200_allgather_fn allgather);
+int b200_comm_rank(void);
+int b200_comm_world(void);
+
 /* Options, to be set before b200_run_main:
  *   "mode"        0 = persistent step kernel when possible (default), 1 = one launch per code object
  *   "max_chunk"   steps per persistent launch
@@ -64,7 +77,7 @@ void b200_request_stop(void);
 int b200_set_option(const char* key, double value);
 
 /* Counters: "launches", "events" (delivered synaptic events), "steps", "h2d_bytes",
- * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "runs", and per
+ * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "grid", "runs", and per
  * Network::run call "run<i>.device_seconds|wall_seconds|upload_seconds|download_seconds|events|
  * steps|persistent".  -1 if unknown. */
 double b200_get_counter(const char* key);

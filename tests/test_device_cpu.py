@@ -57,14 +57,15 @@ def test_device_code_is_sm100a_sass(cuba_project):
 
 def test_barrier_plan_of_cuba(cuba_project):
     """stateupdate -> threshold share the owned partition (no barrier); one barrier before the
-    consumers of the spike list; one at the end of the step."""
+    consumers of the spike list (compaction, monitor, pathways; the resetter only touches the
+    CTA's own segment); one at the end of the step."""
     src = open(os.path.join(cuba_project, "b200_kernels.cu")).read()
     m = re.search(r"schedule: (.*)\n", src)
     assert m
     sched = m.group(1).strip()
     assert sched == ("cuba_P_stateupdater_codeobject cuba_P_spike_thresholder_codeobject | "
                      "cuba_spikes_codeobject cuba_Ce_pre_codeobject cuba_Ci_pre_codeobject "
-                     "cuba_P_spike_resetter_codeobject"), sched
+                     "cuba_P_spike_resetter_codeobject compact_array_cuba_P__spikespace"), sched
     assert "grid barriers per step: 2" in src
 
 
