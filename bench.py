@@ -159,6 +159,11 @@ def run_b200(args, rank, world):
     directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
     t_build0 = time.time()
     b.prefs["devices.b200.persistent"] = not args.stepwise
+    b.prefs["devices.b200.profile_phases"] = bool(args.phases)
+    if args.ctas_per_sm:
+        b.prefs["devices.b200.ctas_per_sm"] = args.ctas_per_sm
+    if args.grid:
+        b.prefs["devices.b200.grid"] = args.grid
     objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs)
     b.device.build(directory=directory, compile=True, run=False, with_output=False)
     build_seconds = time.time() - t_build0
@@ -180,6 +185,10 @@ def run_b200(args, rank, world):
     events = sum(cnt(f"run{r}.events") for r in timed)
     steps = sum(cnt(f"run{r}.steps") for r in timed)
     persistent = all(cnt(f"run{r}.persistent") == 1 for r in timed)
+    if args.phases and rank == 0:
+        total_steps = cnt("steps")
+        for name, cyc in b.device.phase_profile():
+            sys.stderr.write(f"PHASE {name:55s} {cyc / total_steps / 1.965e3:8.3f} us/step\n")
     model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
     n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
     n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
@@ -251,6 +260,10 @@ def main():
     ap.add_argument("--workload", default="cobahh_256k", choices=sorted(WORKLOADS))
     ap.add_argument("--sim-steps", type=int, default=0, help="simulation timesteps per bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning aid: prefs.devices.b200.ctas_per_sm")
+    ap.add_argument("--grid", type=int, default=0, help="tuning aid: prefs.devices.b200.grid (max CTAs)")
+    ap.add_argument("--phases", action="store_true",
+                    help="profiling aid: per-code-object cycle counters inside the persistent kernel")
     ap.add_argument("--stepwise", action="store_true",
                     help="profiling aid: one kernel launch per code object per step (not the product mode)")
     args = ap.parse_args()

@@ -79,7 +79,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
                                              const Ctx& c) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += (unsigned long long)c.nb;
+        target += (unsigned long long)c.gnb;
         if (c.world > 1) __threadfence_system(); else __threadfence();
         atomicAdd(counter, 1ULL);
         while (ld_acquire_u64(counter) < target) {
@@ -117,7 +117,7 @@ __host__ __device__ __forceinline__ int64_t warp_first(int64_t lo, int64_t hi, i
 __device__ __forceinline__ Slice owned_slice(int64_t N, const Ctx& c) {
     int64_t lo, hi;
     rank_range(N, c.rank, c.world, lo, hi);
-    const int64_t g = (int64_t)c.bid * kWarps + (threadIdx.x >> 5), G = (int64_t)c.nb * kWarps;
+    const int64_t g = (int64_t)c.gbid * kWarps + (threadIdx.x >> 5), G = (int64_t)c.gnb * kWarps;
     Slice s;
     s.lo = warp_first(lo, hi, g, G);
     s.hi = warp_first(lo, hi, g + 1, G);
@@ -127,10 +127,10 @@ __device__ __forceinline__ Slice owned_slice(int64_t N, const Ctx& c) {
 __device__ __forceinline__ Slice owned_cta(int64_t N, const Ctx& c) {
     int64_t lo, hi;
     rank_range(N, c.rank, c.world, lo, hi);
-    const int64_t G = (int64_t)c.nb * kWarps;
+    const int64_t G = (int64_t)c.gnb * kWarps;
     Slice s;
-    s.lo = warp_first(lo, hi, (int64_t)c.bid * kWarps, G);
-    s.hi = warp_first(lo, hi, (int64_t)(c.bid + 1) * kWarps, G);
+    s.lo = warp_first(lo, hi, (int64_t)c.gbid * kWarps, G);
+    s.hi = warp_first(lo, hi, (int64_t)(c.gbid + 1) * kWarps, G);
     return s;
 }
 
@@ -169,7 +169,7 @@ __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter
     const int warp = threadIdx.x >> 5;
     const Slice sl = owned_slice(es.N, c);
     const size_t slot_off = (size_t)ring_index(timestep, es.slots) * (size_t)es.seg_stride;
-    const int segi = c.rank * c.nb + c.bid;
+    const int segi = c.rank * c.gnb + c.gbid;
 
     int wtotal = __popcll(mask);
 #pragma unroll
@@ -211,7 +211,7 @@ __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter
 // Multi-GPU: after the grid barrier that follows the thresholder (all CTAs' peer stores are
 // fenced at system scope by then), tell every peer that step `timestep` of this rank is complete.
 __device__ __forceinline__ void publish_done(const Ctx& c, const EventSpaceDev& es, int64_t timestep) {
-    if (c.world > 1 && c.bid == 0 && threadIdx.x == 0) {
+    if (c.world > 1 && c.gbid == 0 && threadIdx.x == 0) {
         __threadfence_system();
         for (int q = 0; q < c.world; ++q)
             if (q != c.rank) st_release_sys_u64(es.peer_done[q], (unsigned long long)(timestep + 1));
@@ -272,8 +272,8 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
     v.seg_start = es.seg_start;
     v.pref = pref;
     const bool local = local_only && c.world > 1;
-    v.seg_lo = local ? c.rank * c.nb : 0;
-    v.nseg = local ? c.nb : es.nseg;
+    v.seg_lo = local ? c.rank * c.gnb : 0;
+    v.nseg = local ? c.gnb : es.nseg;
     const long long tag = ((long long)(es.id * 2 + (local ? 1 : 0) + 1) << 44) ^ (timestep + 1);
     __syncthreads();
     if (*tagp != tag) {

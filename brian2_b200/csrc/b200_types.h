@@ -17,9 +17,14 @@ struct Clk {
 };
 
 // Virtual CTA coordinates (identical in per-code-object kernels and in the persistent kernel)
+// (bid, nb) is the VIRTUAL grid a code object distributes its work over: the whole grid for the
+// per-element code objects (they share one partition), a sub-range of CTAs when several
+// independent code objects of one phase run side by side.  (gbid, gnb) is the real grid.
 struct Ctx {
     int bid;
     int nb;
+    int gbid;
+    int gnb;
     int rank;
     int world;
 };

@@ -31,6 +31,8 @@ from brian2.codegen.permutation_analysis import (
 )
 from brian2.codegen.statements import Statement
 from brian2.core.clocks import Clock
+from brian2.core.preferences import prefs
+from brian2.parsing.rendering import CPPNodeRenderer
 from brian2.core.functions import Function
 from brian2.core.variables import ArrayVariable, Constant
 from brian2.utils.stringtools import (
@@ -46,7 +48,7 @@ __all__ = ["CUDACodeGenerator", "is_eventspace", "clock_field"]
 #: (host only) must not be pasted into device code
 _BUILTIN_DEVICE_FUNCTIONS = {
     "_timestep", "_exprel", "_clip", "_sign", "_brian_abs", "int_", "_b200_int",
-    "_brian_mod", "_brian_floordiv", "_brian_pow",
+    "_brian_mod", "_brian_floordiv", "_brian_pow", "_b200_exp_pow",
 }
 
 
@@ -86,6 +88,29 @@ def _annotate_host_device(code):
     return "\n".join(out)
 
 
+class CUDANodeRenderer(CPPNodeRenderer):
+    """C++ expression renderer with one device-specific rewrite: ``exp(a)**c`` becomes
+    ``_b200_exp_pow(a, c)`` (csrc/b200_functions.cuh) -- see there for the numerics."""
+
+    def __init__(self, auto_vectorise=None, fuse_exp_pow=True):
+        super().__init__(auto_vectorise=auto_vectorise)
+        self.fuse_exp_pow = fuse_exp_pow
+
+    def render_BinOp(self, node):
+        if (
+            self.fuse_exp_pow
+            and node.op.__class__.__name__ == "Pow"
+            and node.left.__class__.__name__ == "Call"
+            and getattr(node.left.func, "id", None) == "exp"
+            and len(node.left.args) == 1
+        ):
+            return (
+                f"_b200_exp_pow({self.render_node(node.left.args[0])}, "
+                f"{self.render_node(node.right)})"
+            )
+        return super().render_BinOp(node)
+
+
 class CUDACodeGenerator(CPPCodeGenerator):
     """CUDA (sm_100a) language for the in-loop code objects of the ``b200`` device."""
 
@@ -100,6 +125,17 @@ class CUDACodeGenerator(CPPCodeGenerator):
         # No __restrict__ on state arrays: inside the persistent kernel the same array is read by
         # one code object and written by another, and ld.global.nc on such data would be stale.
         return " "
+
+    def translate_expression(self, expr):
+        expr = word_substitute(expr, self.func_name_replacements)
+        return (
+            CUDANodeRenderer(
+                auto_vectorise=self.auto_vectorise,
+                fuse_exp_pow=bool(prefs["devices.b200.fuse_exp_pow"]),
+            )
+            .render_expr(expr)
+            .strip()
+        )
 
     def _is_synaptic_effect(self):
         return self.template_name == "synapses"

@@ -91,6 +91,29 @@ prefs.register_preferences(
     ctas_per_sm=BrianPreference(
         default=2, docs="Resident CTAs (512 threads each) per SM used to size all grids."
     ),
+    fuse_exp_pow=BrianPreference(
+        default=True,
+        docs="""
+        Evaluate ``exp(a)**c`` (|c| <= 1) in device code as one exponential of the double-double
+        product ``a*c`` instead of ``pow(exp(a), c)``.  Both are within ~0.5 ulp of the true value
+        (the reference's glibc result is, too); the fused form costs a third.
+        """,
+    ),
+    split_phases=BrianPreference(
+        default=True,
+        docs="""
+        Inside the persistent kernel, run the mutually independent code objects of one phase
+        (monitors, synaptic pathways, compaction) side by side on disjoint sets of CTAs instead
+        of one after the other on all CTAs.
+        """,
+    ),
+    profile_phases=BrianPreference(
+        default=False,
+        docs="""
+        Instrument the persistent kernel: CTA 0 accumulates the SM cycles it spends in every code
+        object and at every grid barrier (read back with ``device.phase_profile()``).
+        """,
+    ),
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
@@ -333,9 +356,7 @@ class B200Device(CPPStandaloneDevice):
         template = info["template"]
         kw = info["template_kwds"]
         # "owned": every element is touched only by the CTA that owns it in the common partition
-        owned = template in ("stateupdate", "threshold", "reset") or (
-            template == "statemonitor" and kw.get("b200_source_size") is not None
-        )
+        owned = self._is_owned_type(codeobj)
         priv_r = set(acc["read"]) if owned else set()
         priv_w = set(acc["write"]) if owned else set()
         shared_r = set(acc["scattered_read"]) | (set() if owned else set(acc["read"]))
@@ -382,7 +403,7 @@ class B200Device(CPPStandaloneDevice):
         ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
         ph_thresholders = []   # event spaces written since the last barrier (multi-GPU publish)
 
-        def add(name, kind, pr, pw, sr, sw, extra=None):
+        def add(name, kind, pr, pw, sr, sw, extra=None, owned=False):
             nonlocal ph_pr, ph_pw, ph_sr, ph_sw, ph_thresholders
             conflict = bool(
                 (sw | pw) & (ph_sr | ph_sw)      # I write what somebody read/wrote (shared)
@@ -390,7 +411,8 @@ class B200Device(CPPStandaloneDevice):
                 or (sr | pr) & ph_sw              # I read what somebody wrote (shared)
                 or sr & ph_pw                     # shared read of a privately written array
             )
-            item = {"name": name, "kind": kind, "barrier": conflict and len(items) > 0, "publish": []}
+            item = {"name": name, "kind": kind, "barrier": conflict and len(items) > 0, "publish": [],
+                    "owned": owned, "share": None}
             if conflict:
                 item["publish"] = list(ph_thresholders)
                 ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
@@ -417,7 +439,8 @@ class B200Device(CPPStandaloneDevice):
             if info["template"] == "synapses_push_spikes":
                 continue
             pr, pw, sr, sw = self._codeobj_access(codeobj)
-            add(codeobj.name, "codeobj", pr, pw, sr, sw)
+            add(codeobj.name, "codeobj", pr, pw, sr, sw, owned=self._is_owned_type(codeobj),
+                extra={"weight": 6 if info["template"] == "synapses" else 1})
             if info["template"] == "threshold":
                 es = info["template_kwds"]["eventspace_variable"]
                 ph_thresholders.append(
@@ -425,7 +448,32 @@ class B200Device(CPPStandaloneDevice):
                 )
         # event spaces still unpublished at the end of the step go out with the end-of-step barrier
         self._b200_tail_publish = list(ph_thresholders)
+        # Side-by-side execution: the code objects of one phase are mutually independent (that is
+        # what "no barrier between them" means), and the ones that are not tied to the element
+        # partition are short latency chains -- each gets its own share of the CTAs instead of
+        # all CTAs walking through them one after the other.
+        if prefs.devices.b200.split_phases:
+            phase = []
+            for item in items + [None]:
+                if item is None or item["barrier"]:
+                    free = [it for it in phase if not it["owned"]]
+                    if len(free) > 1:
+                        total = sum(it.get("weight", 1) for it in free)
+                        acc = 0
+                        for it in free:
+                            w = it.get("weight", 1)
+                            it["share"] = (acc, acc + w, total)
+                            acc += w
+                    phase = []
+                if item is not None:
+                    phase.append(item)
         return items
+
+    def _is_owned_type(self, codeobj):
+        info = self._b200_info[codeobj.name]
+        return info["template"] in ("stateupdate", "threshold", "reset") or (
+            info["template"] == "statemonitor" and info["template_kwds"].get("b200_source_size") is not None
+        )
 
     # ------------------------------------------------------------------------------------------
     # monitors
@@ -737,6 +785,7 @@ class B200Device(CPPStandaloneDevice):
             user_headers=user_headers,
             profiled=bool(self.enable_profiling_any),
             ctas_per_sm=int(prefs.devices.b200.ctas_per_sm),
+            profile_phases=bool(prefs.devices.b200.profile_phases),
         )
         writer.write("b200_kernels.cu", kernels)
         self.cu_source_files = ["b200_kernels.cu"]
@@ -830,6 +879,18 @@ class B200Device(CPPStandaloneDevice):
             )
         finally:
             _ref_device_module.subprocess = original
+
+    def phase_profile(self, plan=0):
+        """[(phase name, SM cycles spent by CTA 0)] of the persistent kernel of run() call `plan`
+        (needs ``prefs.devices.b200.profile_phases = True`` at build time)."""
+        info = self._b200_plan_info[plan]
+        if info["alias"] is not None:
+            info = self._b200_plan_info[info["alias"]]
+        names = []
+        for it in info["entries"]:
+            names += ["barrier" if it["barrier"] else None, it["name"]]
+        names.append("end-of-step barrier")
+        return [(n, self.counter(f"phase{i}")) for i, n in enumerate(names) if n is not None]
 
     # counters of the last run (for benchmarks)
     def counter(self, key):

@@ -87,14 +87,14 @@ int _b200_grid_size()
 __global__ void __launch_bounds__(b200::kBlock)
 _kernel_b200_compact{{es.name}}(const _B200Clocks _clks)
 {
-    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     b200::view_reset();
     b200::compact_segments(_A._es{{es.name}}, _clks.{{es.clock}}.timestep, _ctx, _A._ctrl);
 }
 B200_REGISTER_KERNEL(_kernel_b200_compact{{es.name}})
 __global__ void _kernel_b200_publish{{es.name}}(const _B200Clocks _clks)
 {
-    const b200::Ctx _ctx{0, 1, _A._rank, _A._world};
+    const b200::Ctx _ctx{0, 1, 0, 1, _A._rank, _A._world};
     b200::publish_done(_ctx, _A._es{{es.name}}, _clks.{{es.clock}}.timestep);
 }
 void _run_b200_compact{{es.name}}()
@@ -134,12 +134,18 @@ struct _B200Scal_{{plan.index}} {
 __global__ void __launch_bounds__(b200::kBlock)
 _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
 {
-    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     unsigned long long _bar_target = 0ULL;
     __shared__ int _s_stop;
     _B200Clocks _clks = _clks0;
     long long _step = 0;
     b200::view_reset();
+    {% if profile_phases %}
+    long long _pt = clock64();
+    #define B200_PHASE(i) if (_ctx.bid == 0 && threadIdx.x == 0) { const long long _now = clock64(); _A._prof[i] += (unsigned long long)(_now - _pt); _pt = _now; }
+    {% else %}
+    #define B200_PHASE(i)
+    {% endif %}
     while (_step < _nsteps)
     {
         if (_ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
@@ -147,19 +153,38 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         {% for item in plan.entries %}
         {% if item.barrier %}
         b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        B200_PHASE({{2 * loop.index0}})
         {% for pub in item.publish %}
         b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
         {% endfor %}
         {% elif not loop.first %}
         __syncthreads();
         {% endif %}
-        {% if item.kind == 'compact' %}
+        {% if item.share %}
+        {   // CTAs [{{item.share[0]}}/{{item.share[2]}}, {{item.share[1]}}/{{item.share[2]}}) of the grid
+            int _lo = (int)(((long long)_ctx.gnb * {{item.share[0]}}) / {{item.share[2]}});
+            int _hi = (int)(((long long)_ctx.gnb * {{item.share[1]}}) / {{item.share[2]}});
+            if (_lo >= _ctx.gnb) _lo = _ctx.gnb - 1;
+            if (_hi <= _lo) _hi = _lo + 1;
+            if (_ctx.gbid >= _lo && _ctx.gbid < _hi)
+            {
+                const b200::Ctx _sub{_ctx.gbid - _lo, _hi - _lo, _ctx.gbid, _ctx.gnb, _ctx.rank, _ctx.world};
+                {% if item.kind == 'compact' %}
+                b200::compact_segments(_A._es{{item.es}}, _clks.{{item.clock}}.timestep, _sub, _A._ctrl);
+                {% else %}
+                _dev_{{item.name}}(_sub, _clks, _sc.{{item.name}});
+                {% endif %}
+            }
+        }
+        {% elif item.kind == 'compact' %}
         b200::compact_segments(_A._es{{item.es}}, _clks.{{item.clock}}.timestep, _ctx, _A._ctrl);
         {% else %}
         _dev_{{item.name}}(_ctx, _clks, _sc.{{item.name}});
         {% endif %}
+        B200_PHASE({{2 * loop.index0 + 1}})
         {% endfor %}
         b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        B200_PHASE({{2 * (plan.entries | length)}})
         {% for pub in plan.tail_publish %}
         b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
         {% endfor %}
@@ -175,7 +200,16 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     }
     if (_ctx.bid == 0 && threadIdx.x == 0) _A._ctrl->steps_done = (int)_step;
 }
+#undef B200_PHASE
 B200_REGISTER_KERNEL(_b200_persistent_{{plan.index}})
+{% if profile_phases %}
+// names of the profiled phases of plan #{{plan.index}} (index = slot in _A._prof)
+const char* _b200_phase_names_{{plan.index}}[] = {
+    {% for item in plan.entries %}
+    "{{ 'barrier' if item.barrier else '-' }}", "{{item.name}}",
+    {% endfor %}
+    "end-of-step barrier", 0 };
+{% endif %}
 
 static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
 {

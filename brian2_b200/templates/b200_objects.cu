@@ -27,6 +27,7 @@ struct _B200Arrays {
     {% endif %}
     {% endfor %}
     int _rank, _world;
+    unsigned long long* _prof;     // per-phase cycle counters of the persistent kernel (optional)
     {% for es in b200_eventspaces %}
     b200::EventSpaceDev _es{{es.name}};
     {% endfor %}
@@ -150,6 +151,10 @@ void _b200_upload()
     {% endfor %}
     // event spaces (history survives between runs); on several GPUs the rings are mapped into
     // every peer once per allocation (CUDA IPC handles travel through the allgather callback)
+    if (!_A_host._prof) {
+        _A_host._prof = (unsigned long long*)b200::dev_alloc(512 * sizeof(unsigned long long));
+        B200_CUDA(cudaMemset(_A_host._prof, 0, 512 * sizeof(unsigned long long)));
+    }
     _A_host._rank = st.rank;
     _A_host._world = st.world;
     {% for es in b200_eventspaces %}

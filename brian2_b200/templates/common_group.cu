@@ -48,7 +48,7 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}(const b200::Ctx& _ctx, con
 __global__ void __launch_bounds__(b200::kBlock)
 _kernel_{{codeobj_name}}(const _B200Clocks _clks, const _co_{{codeobj_name}}::Scal _sc)
 {
-    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     b200::view_reset();
     _dev_{{codeobj_name}}(_ctx, _clks, _sc);
 }

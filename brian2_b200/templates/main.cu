@@ -159,6 +159,13 @@ double b200_get_counter(const char* key)
     if (k == "num_sms") return (double)st.num_sms;
     if (k == "grid") return st.initialised ? (double)_b200_grid_size() : 0.0;
     if (k == "runs") return (double)Network::_b200_run_log.size();
+    if (k.compare(0, 5, "phase") == 0) {   // "phase<i>": cycles CTA 0 spent in phase i (profile_phases)
+        const int i = atoi(k.c_str() + 5);
+        unsigned long long v = 0;
+        if (i < 0 || i >= 512 || !_A_host._prof) return -1.0;
+        cudaMemcpy(&v, _A_host._prof + i, sizeof(v), cudaMemcpyDeviceToHost);
+        return (double)v;
+    }
     // per-run records: "run<i>.<field>"
     if (k.compare(0, 3, "run") == 0) {
         const size_t dot = k.find('.');

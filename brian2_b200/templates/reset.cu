@@ -6,7 +6,7 @@
 {% block maincode %}
     const b200::EventSpaceDev& _es = _A._es{{get_array_name(eventspace_variable, access_data=False)}};
     const int32_t* _slot = _es.seg + (size_t)b200::ring_index(_clks.{{b200_clock}}.timestep, _es.slots) * (size_t)_es.seg_stride;
-    const int _segi = _ctx.rank * _ctx.nb + _ctx.bid;
+    const int _segi = _ctx.rank * _ctx.gnb + _ctx.gbid;
     const int32_t _num_events = _slot[_es.N + _segi];
     const int32_t* _events = _slot + _es.seg_start[_segi];
     {{scalar_code|autoindent}}
