@@ -81,7 +81,7 @@ inline void runtime_init() {
             "b200 device: no CUDA device available (this device has no CPU fallback)");
     // one process per GPU: rank/world come from b200_set_comm; the device from LOCAL_RANK
     const char* lr = getenv("LOCAL_RANK");
-    s.device = (s.world > 1 && lr) ? atoi(lr) % ndev : 0;
+    s.device = lr ? atoi(lr) % ndev : 0;
     if (s.world > kMaxRanks) throw std::runtime_error("b200: at most 8 ranks (GPUs of one box)");
     if (s.world > 1 && !s.allgather)
         throw std::runtime_error("b200: world > 1 needs an allgather callback (b200_set_comm)");

@@ -91,6 +91,15 @@ prefs.register_preferences(
     ctas_per_sm=BrianPreference(
         default=2, docs="Resident CTAs (512 threads each) per SM used to size all grids."
     ),
+    multi_gpu=BrianPreference(
+        default=True,
+        docs="""
+        Shard the network over all ranks of the initialised ``torch.distributed`` process group
+        (one process per GPU, partition by postsynaptic neuron, spike lists exchanged by NVLink
+        peer stores).  If False -- or if there is no process group -- every process simulates the
+        whole network on its own GPU.
+        """,
+    ),
     fuse_exp_pow=BrianPreference(
         default=True,
         docs="""
@@ -146,6 +155,9 @@ class B200Device(CPPStandaloneDevice):
         self._b200_seed = None
         self._b200_library = None
         self._b200_run_counter = 0
+        #: out-of-band communicator of a multi-GPU run (brian2_b200.multigpu.Communicator)
+        self._b200_comm = getattr(self, "_b200_comm", None)
+        self._b200_written_vars = set()
         self.cu_source_files = []
 
     # ------------------------------------------------------------------------------------------
@@ -556,6 +568,7 @@ class B200Device(CPPStandaloneDevice):
             for var in codeobj.variables.values():
                 if isinstance(var, ArrayVariable) and self.get_array_name(var, access_data=False) in names:
                     written.add(var)
+        self._b200_written_vars = set(written)
         monitor_of, min_cap = {}, {}
         for mon in monitors:
             for b in mon["buffers"]:
@@ -859,11 +872,139 @@ class B200Device(CPPStandaloneDevice):
         lib.set_option("max_chunk", int(prefs.devices.b200.max_chunk))
         lib.set_option("ctas_per_sm", int(prefs.devices.b200.ctas_per_sm))
         lib.set_option("grid", int(prefs.devices.b200.grid))
+        comm = self.communicator()
+        if comm.world > 1:
+            self._check_multi_gpu_support()
+            lib.set_comm(comm.rank, comm.world, comm.allgather)
         self._b200_library = lib
         status = lib.run_main(args, stdout=stdout)
         if status != 0:
             sys.stderr.write(f"b200 run failed: {lib.last_error()}\n")
         return status
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU (one process per GPU): communicator, support check, merge of the results
+    # ------------------------------------------------------------------------------------------
+    def set_communicator(self, comm):
+        """Use ``comm`` (`brian2_b200.multigpu.Communicator`) instead of the default, which is
+        built on the initialised ``torch.distributed`` process group."""
+        self._b200_comm = comm
+
+    def communicator(self):
+        from .multigpu import Communicator, default_communicator
+
+        if self._b200_comm is not None:
+            return self._b200_comm
+        if not prefs.devices.b200.multi_gpu:
+            return Communicator()
+        return default_communicator()
+
+    def _check_multi_gpu_support(self):
+        """The partition by postsynaptic neuron keeps every write local as long as synaptic code
+        writes synaptic and postsynaptic variables only."""
+        from brian2.synapses.synapses import Synapses
+
+        for codeobj in self.code_objects.values():
+            info = self._b200_info.get(codeobj.name)
+            if info is None:
+                continue
+            template, owner = info["template"], info["owner"]
+            if template == "stateupdate" and isinstance(owner, Synapses):
+                raise NotImplementedError("b200 multi-GPU: clock-driven synaptic equations")
+            if template == "statemonitor" and info["template_kwds"].get("b200_source_size") is None:
+                raise NotImplementedError("b200 multi-GPU: StateMonitor of synapses or subgroups")
+            if template == "synapses":
+                acc = self._b200_access.get(codeobj.name, {})
+                if acc.get("serial"):
+                    raise NotImplementedError("b200 multi-GPU: order-dependent synaptic code")
+                pathway = info["template_kwds"]["pathway"]
+                pre_idx = "_presynaptic_idx" if pathway.prepost == "pre" else "_postsynaptic_idx"
+                for name in codeobj.variables:
+                    if codeobj.variable_indices[name] == "_presynaptic_idx":
+                        var = codeobj.variables[name]
+                        if isinstance(var, ArrayVariable) and var in self._b200_written_vars:
+                            raise NotImplementedError(
+                                f"b200 multi-GPU: synaptic code of '{pathway.name}' accesses the "
+                                f"presynaptic variable '{name}' that changes during the run"
+                            )
+
+    def _merge_multi_gpu_results(self, comm):
+        """Combine the per-rank results (see brian2_b200/multigpu.py) into ``array_cache``."""
+        from brian2.groups.neurongroup import NeuronGroup
+        from brian2.monitors.ratemonitor import PopulationRateMonitor
+        from brian2.monitors.spikemonitor import EventMonitor
+        from brian2.monitors.statemonitor import StateMonitor
+        from brian2.synapses.synapses import Synapses
+
+        from . import multigpu as mg
+
+        world = comm.world
+        local = lambda var: CPPStandaloneDevice.get_value(self, var)
+        merged = {}
+        by_owner = defaultdict(list)
+        for var in sorted(self._b200_written_vars, key=lambda v: self.arrays[v]):
+            if clock_field(var) is not None or is_eventspace(var):
+                continue
+            try:
+                by_owner[var.owner.name].append(var)
+            except ReferenceError:
+                continue
+        owners = {}
+        for codeobj in self.code_objects.values():
+            info = self._b200_info.get(codeobj.name)
+            if info is not None:
+                owners[info["owner"].name] = info["owner"]
+        # objects reach this point in the same (sorted) order on every rank
+        for owner_name in sorted(by_owner):
+            variables = by_owner[owner_name]
+            owner = owners.get(owner_name)
+            if owner is None:   # e.g. a NeuronGroup only written through synapses
+                owner = variables[0].owner
+            if isinstance(owner, EventMonitor):
+                rec = {v.name: local(v) for v in variables if v.name not in ("N", "count")}
+                parts = comm.allgather_object(rec)
+                t_parts = [p["t"] for p in parts]
+                t_all, cols = mg.merge_spike_records(t_parts, {k: [p[k] for p in parts] for k in rec if k != "t"})
+                for v in variables:
+                    if v.name == "t":
+                        merged[v] = t_all
+                    elif v.name in cols:
+                        merged[v] = cols[v.name]
+                    elif v.name == "count":
+                        merged[v] = np.sum(np.stack(comm.allgather_object(local(v))), axis=0).astype(v.dtype)
+                    elif v.name == "N":
+                        merged[v] = np.array([len(t_all)], dtype=v.dtype)
+            elif isinstance(owner, StateMonitor):
+                indices = np.asarray(owner.variables["_indices"].get_value())
+                for v in variables:
+                    if getattr(v, "ndim", 1) == 2:
+                        parts = comm.allgather_object(local(v))
+                        merged[v] = mg.merge_state_columns(parts, indices, len(owner.source), world)
+            elif isinstance(owner, PopulationRateMonitor):
+                for v in variables:
+                    if v.name == "rate":
+                        parts = comm.allgather_object(local(v))
+                        merged[v] = mg.merge_rate(parts, float(owner.clock.dt_), len(owner.source))
+            elif isinstance(owner, Synapses):
+                post = local(owner.variables["_synaptic_post"])
+                target = owner.target
+                n_parent = len(getattr(target, "source", target))
+                own = mg.owner_of(post, n_parent, world)
+                for v in variables:
+                    if getattr(v, "scalar", False):
+                        continue
+                    parts = comm.allgather_object(local(v))
+                    merged[v] = mg.merge_by_owner(parts, own)
+            elif isinstance(owner, NeuronGroup):
+                for v in variables:
+                    if getattr(v, "scalar", False):
+                        continue
+                    parts = comm.allgather_object(local(v))
+                    merged[v] = mg.merge_by_block(parts, len(owner), world)
+        for v, value in merged.items():
+            self.array_cache[v] = value
+            if isinstance(v, DynamicArrayVariable) and getattr(v, "ndim", 1) == 1:
+                v.size = len(value)
 
     def run(self, directory=None, results_directory=None, with_output=True, run_args=None):
         import brian2.devices.cpp_standalone.device as _ref_device_module
@@ -879,6 +1020,9 @@ class B200Device(CPPStandaloneDevice):
             )
         finally:
             _ref_device_module.subprocess = original
+        comm = self.communicator()
+        if comm.world > 1:
+            self._merge_multi_gpu_results(comm)
 
     def phase_profile(self, plan=0):
         """[(phase name, SM cycles spent by CTA 0)] of the persistent kernel of run() call `plan`

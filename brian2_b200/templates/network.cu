@@ -177,6 +177,9 @@ void Network::run(const double duration, void (*report_func)(const double, const
     B200_CUDA(cudaEventRecord(_ev_stop, b200::state().stream));
     B200_CUDA(cudaStreamSynchronize(b200::state().stream));
     B200_CUDA(cudaDeviceSynchronize());
+    // several GPUs: nobody touches its rings (download, next upload) while a peer may still be
+    // storing spikes into them
+    b200::host_barrier();
     Network::_globally_running = false;
     current = hrc::now();
     elapsed_realtime = std::chrono::duration<double>(current - start).count();

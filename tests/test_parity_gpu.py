@@ -56,3 +56,28 @@ def test_spike_exact_stepwise(brian, project_dir, case):
                                  prefs_update={"devices.b200.persistent": False}, **kwds)
     _check(case, res, True)
     brian.prefs["devices.b200.persistent"] = True
+
+
+def _gpu_count():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_sharded_parity():
+    """The same golden vectors with the network partitioned by postsynaptic neuron over 2 GPUs
+    (spike lists exchanged by NVLink peer stores inside the persistent kernel)."""
+    import subprocess
+    import sys
+
+    n = min(_gpu_count(), 2)
+    script = os.path.join(os.path.dirname(__file__), "run_multigpu_case.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", script,
+           "cuba_1000", "brunel_hetero", "brunel_homog", "cobahh_1000", "stdp_1000", "synapses_only_delay"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    assert "MULTIGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
