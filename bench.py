@@ -106,10 +106,12 @@ def _import_brian():
     return b
 
 
-def _build_script(b, workload, device_name, directory, sim_steps, n_runs, openmp_threads=0, strict=True):
+def _build_script(b, workload, device_name, directory, sim_steps, n_runs, openmp_threads=0, strict=True,
+                  scale=1):
     import models
 
     model, kwds, _, _ = WORKLOADS[workload]
+    kwds = _scaled(kwds, scale)
     import gc
 
     gc.collect()
@@ -134,6 +136,20 @@ def _build_script(b, workload, device_name, directory, sim_steps, n_runs, openmp
     return objs
 
 
+def _scaled(kwds, scale):
+    """Weak scaling: `scale` x the neurons, same number of synapses per neuron."""
+    kwds = dict(kwds)
+    if scale > 1:
+        if "N" in kwds:
+            if "p" in kwds:
+                kwds["p"] = kwds["p"] / scale
+            kwds["N"] = kwds["N"] * scale
+        elif "N_E" in kwds:
+            kwds["N_E"] = kwds["N_E"] * scale
+            kwds["epsilon"] = kwds["epsilon"] / scale
+    return kwds
+
+
 def _outdegree_events(b, objs, t_from):
     """Synaptic events in [t_from, end): sum over recorded spikes of the out-degree of the
     spiking neuron over every pathway listening to it."""
@@ -154,17 +170,21 @@ def _outdegree_events(b, objs, t_from):
 
 def run_b200(args, rank, world):
     b = _import_brian()
+    if world > 1:
+        _barrier(world)   # initialises the process group: the device shards over its ranks
     sim_steps = args.sim_steps or 500
     n_runs = args.warmup + args.steps
     directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
     t_build0 = time.time()
+    b.prefs["devices.b200.multi_gpu"] = not args.replicas
     b.prefs["devices.b200.persistent"] = not args.stepwise
     b.prefs["devices.b200.profile_phases"] = bool(args.phases)
     if args.ctas_per_sm:
         b.prefs["devices.b200.ctas_per_sm"] = args.ctas_per_sm
     if args.grid:
         b.prefs["devices.b200.grid"] = args.grid
-    objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs)
+    scale = 1 if args.replicas else world
+    objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs, scale=scale)
     b.device.build(directory=directory, compile=True, run=False, with_output=False)
     build_seconds = time.time() - t_build0
 
@@ -185,10 +205,14 @@ def run_b200(args, rank, world):
     events = sum(cnt(f"run{r}.events") for r in timed)
     steps = sum(cnt(f"run{r}.steps") for r in timed)
     persistent = all(cnt(f"run{r}.persistent") == 1 for r in timed)
-    if args.phases and rank == 0:
+    if args.phases and world > 1:
+        n = max(cnt("polls"), 1.0)
+        sys.stderr.write(f"POLL rank {rank}: {int(n)} sampled waits, spin {cnt('poll_cycles') / n / 1.965e3:.3f} us, "
+                         f"acquire fence {cnt('fence_cycles') / n / 1.965e3:.3f} us per wait\n")
+    if args.phases:
         total_steps = cnt("steps")
         for name, cyc in b.device.phase_profile():
-            sys.stderr.write(f"PHASE {name:55s} {cyc / total_steps / 1.965e3:8.3f} us/step\n")
+            sys.stderr.write(f"PHASE r{rank} {name:55s} {cyc / total_steps / 1.965e3:8.3f} us/step\n")
     model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
     n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
     n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
@@ -260,6 +284,9 @@ def main():
     ap.add_argument("--workload", default="cobahh_256k", choices=sorted(WORKLOADS))
     ap.add_argument("--sim-steps", type=int, default=0, help="simulation timesteps per bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N>1: every rank simulates its own copy of the network instead of sharding one "
+                         "N-times larger network over the ranks")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning aid: prefs.devices.b200.ctas_per_sm")
     ap.add_argument("--grid", type=int, default=0, help="tuning aid: prefs.devices.b200.grid (max CTAs)")
     ap.add_argument("--phases", action="store_true",
@@ -308,11 +335,16 @@ def main():
     value = events / dev_s
     e2e_value = events / e2e_s
     timesteps = r["timesteps"]
-    algo_bytes = timesteps * r["n_neurons"] * bytes_neuron + r["events"] * bytes_event
+    # per-GPU roofline (rank 0): the neurons it owns and the synaptic events it delivered
+    n_owned = r["n_neurons"] / (1 if (args.replicas or world == 1) else world)
+    algo_bytes = timesteps * n_owned * bytes_neuron + r["events"] * bytes_event
     achieved = algo_bytes / r["dev_s"] / 1e9
     config.update({
         "timesteps_per_step": r["sim_steps"], "neurons": r["n_neurons"], "synapses": r["n_syn"],
-        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+        "parallelism": "1 GPU" if world == 1 else (
+            f"{world} independent replicas (one per GPU)" if args.replicas else
+            f"one network of {world}x the neurons (same synapses per neuron) partitioned by postsynaptic "
+            f"neuron over {world} GPUs; spike lists exchanged by NVLink peer stores inside the persistent kernel"),
         "execution": "persistent cooperative step kernel" if r["persistent"] else "one launch per code object",
         "build_seconds": round(r["build_seconds"], 1),
     })
@@ -321,8 +353,8 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
-        "realtime_factor": timesteps * 1e-4 / r["dev_s"],
-        "us_per_timestep": 1e6 * r["dev_s"] / max(timesteps, 1),
+        "realtime_factor": timesteps * 1e-4 / dev_s,
+        "us_per_timestep": 1e6 * dev_s / max(timesteps, 1),
         "clocks": r["clocks"],
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": r["h2d"],
                 "d2h_bytes_per_step": r["d2h"]},

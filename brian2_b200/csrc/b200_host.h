@@ -51,6 +51,7 @@ struct RuntimeState {
     // multi-GPU plumbing: set through b200_set_comm (include/brian2_b200.h) before b200_run_main
     int (*allgather)(const void* send, void* recv, size_t nbytes_per_rank) = nullptr;
     unsigned long long launches = 0;   // kernels launched inside run loops
+    double poll_cycles = 0, fence_cycles = 0, polls = 0;   // multi-GPU wait diagnostics
     double upload_seconds = 0.0, download_seconds = 0.0;
     size_t h2d_bytes = 0, d2h_bytes = 0;
 };
@@ -165,15 +166,15 @@ inline void host_barrier() {
 // later) as the reference's compact `_spikespace` layout -- see EventSpaceDev in b200_types.h.
 // ---------------------------------------------------------------------------------------------
 struct EventSpace {
-    int32_t* seg = nullptr;
-    int32_t* compact = nullptr;
+    unsigned long long* ids = nullptr;   // [slots][N]     tagged ids, per-CTA segments
+    int32_t* cnt = nullptr;              // [slots][nseg]  tagged segment counts
+    int32_t* compact = nullptr;          // [slots][N+1]   reference layout
     int32_t* seg_start = nullptr;
-    unsigned long long* done = nullptr;
     int slots = 0, N = 0, nb = 0, nseg = 0, id = 0;
     int max_delay = 0;         // over all pathways reading this event space
     int min_delay = 1 << 30;   // ditto (1<<30: no pathway)
-    void* peer_seg[kMaxRanks] = {0};
-    void* peer_done[kMaxRanks] = {0};
+    void* peer_ids[kMaxRanks] = {0};
+    void* peer_cnt[kMaxRanks] = {0};
     bool peers_open = false;
 
     void require(int dmin, int dmax) {
@@ -190,43 +191,45 @@ struct EventSpace {
 
     void close_peers() {
         for (int q = 0; q < kMaxRanks; ++q) {
-            if (peer_seg[q] && q != state().rank) cudaIpcCloseMemHandle(peer_seg[q]);
-            if (peer_done[q] && q != state().rank) cudaIpcCloseMemHandle(peer_done[q]);
-            peer_seg[q] = peer_done[q] = nullptr;
+            if (peer_ids[q] && q != state().rank) cudaIpcCloseMemHandle(peer_ids[q]);
+            if (peer_cnt[q] && q != state().rank) cudaIpcCloseMemHandle(peer_cnt[q]);
+            peer_ids[q] = peer_cnt[q] = nullptr;
         }
         peers_open = false;
+    }
+
+    template <typename T>
+    static T* realloc_ring(T* old, int old_slots, size_t old_stride, int new_slots, size_t new_stride,
+                           int64_t timestep, bool keep) {
+        T* nd = (T*)dev_alloc((size_t)new_slots * new_stride * sizeof(T));
+        B200_CUDA(cudaMemset(nd, 0, (size_t)new_slots * new_stride * sizeof(T)));
+        if (old && keep) {
+            // same layout: carry the history of the last steps over (slots only ever grow)
+            for (int back = 1; back <= old_slots && back < new_slots; ++back) {
+                const int64_t s = timestep - back;
+                int64_t os = s % old_slots, ns = s % new_slots;
+                if (os < 0) os += old_slots;
+                if (ns < 0) ns += new_slots;
+                B200_CUDA(cudaMemcpy(nd + ns * new_stride, old + os * old_stride, old_stride * sizeof(T),
+                                     cudaMemcpyDeviceToDevice));
+            }
+        }
+        dev_free(old);
+        return nd;
     }
 
     // (re)allocate; keeps the history of the last steps before `timestep`
     void ensure(int N_, int nb_, int64_t timestep) {
         RuntimeState& st = state();
         const int need = required_slots();
-        if (seg && slots >= need && N == N_ && nb == nb_) return;
-        const int new_slots = need;
+        if (ids && slots >= need && N == N_ && nb == nb_) return;
         const int new_nseg = st.world * nb_;
-        const size_t seg_stride = (size_t)N_ + new_nseg;
-        int32_t* nseg_ = (int32_t*)dev_alloc((size_t)new_slots * seg_stride * sizeof(int32_t));
-        int32_t* ncomp = (int32_t*)dev_alloc((size_t)new_slots * ((size_t)N_ + 1) * sizeof(int32_t));
-        B200_CUDA(cudaMemset(nseg_, 0, (size_t)new_slots * seg_stride * sizeof(int32_t)));
-        B200_CUDA(cudaMemset(ncomp, 0, (size_t)new_slots * ((size_t)N_ + 1) * sizeof(int32_t)));
-        if (seg && N == N_ && nb == nb_) {
-            // same segmentation: carry the history over (slots only ever grow)
-            const size_t old_stride = (size_t)N + nseg;
-            for (int back = 1; back <= slots && back < new_slots; ++back) {
-                const int64_t s = timestep - back;
-                int64_t os = s % slots, ns = s % new_slots;
-                if (os < 0) os += slots;
-                if (ns < 0) ns += new_slots;
-                B200_CUDA(cudaMemcpy(nseg_ + ns * seg_stride, seg + os * old_stride,
-                                     old_stride * sizeof(int32_t), cudaMemcpyDeviceToDevice));
-                B200_CUDA(cudaMemcpy(ncomp + ns * ((size_t)N_ + 1), compact + os * ((size_t)N + 1),
-                                     ((size_t)N + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice));
-            }
-        }
+        const bool keep = ids && N == N_ && nb == nb_;
         close_peers();
-        dev_free(seg); dev_free(compact);
-        seg = nseg_; compact = ncomp;
-        slots = new_slots; N = N_; nb = nb_; nseg = new_nseg;
+        ids = realloc_ring(ids, slots, (size_t)N, need, (size_t)N_, timestep, keep);
+        cnt = realloc_ring(cnt, slots, (size_t)nseg, need, (size_t)new_nseg, timestep, keep);
+        compact = realloc_ring(compact, slots, (size_t)N + 1, need, (size_t)N_ + 1, timestep, keep);
+        slots = need; N = N_; nb = nb_; nseg = new_nseg;
         // first neuron of every segment (same arithmetic as owned_cta on the device)
         std::vector<int32_t> start(nseg + 1);
         for (int q = 0; q < st.world; ++q) {
@@ -239,10 +242,6 @@ struct EventSpace {
         dev_free(seg_start);
         seg_start = (int32_t*)dev_alloc((nseg + 1) * sizeof(int32_t));
         B200_CUDA(cudaMemcpy(seg_start, start.data(), (nseg + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-        if (!done) {
-            done = (unsigned long long*)dev_alloc(kMaxRanks * sizeof(unsigned long long));
-            B200_CUDA(cudaMemset(done, 0, kMaxRanks * sizeof(unsigned long long)));
-        }
     }
 
     static void rank_range_host(int64_t N, int rank, int world, int64_t& lo, int64_t& hi) {
@@ -257,19 +256,19 @@ struct EventSpace {
         return e < hi ? e : hi;
     }
 
-    // multi-GPU: map every peer's ring and `done` counters (CUDA IPC, one exchange per allocation)
+    // multi-GPU: map every peer's ring (CUDA IPC, one handle exchange per allocation)
     void open_peers() {
         RuntimeState& st = state();
         if (st.world <= 1 || peers_open) return;
         B200_CUDA(cudaDeviceSynchronize());
-        struct Handles { cudaIpcMemHandle_t seg, done; } mine, all[kMaxRanks];
-        B200_CUDA(cudaIpcGetMemHandle(&mine.seg, seg));
-        B200_CUDA(cudaIpcGetMemHandle(&mine.done, done));
+        struct Handles { cudaIpcMemHandle_t ids, cnt; } mine, all[kMaxRanks];
+        B200_CUDA(cudaIpcGetMemHandle(&mine.ids, ids));
+        B200_CUDA(cudaIpcGetMemHandle(&mine.cnt, cnt));
         host_allgather(&mine, all, sizeof(Handles));
         for (int q = 0; q < st.world; ++q) {
-            if (q == st.rank) { peer_seg[q] = seg; peer_done[q] = done; continue; }
-            B200_CUDA(cudaIpcOpenMemHandle(&peer_seg[q], all[q].seg, cudaIpcMemLazyEnablePeerAccess));
-            B200_CUDA(cudaIpcOpenMemHandle(&peer_done[q], all[q].done, cudaIpcMemLazyEnablePeerAccess));
+            if (q == st.rank) { peer_ids[q] = ids; peer_cnt[q] = cnt; continue; }
+            B200_CUDA(cudaIpcOpenMemHandle(&peer_ids[q], all[q].ids, cudaIpcMemLazyEnablePeerAccess));
+            B200_CUDA(cudaIpcOpenMemHandle(&peer_cnt[q], all[q].cnt, cudaIpcMemLazyEnablePeerAccess));
         }
         peers_open = true;
     }
@@ -278,15 +277,14 @@ struct EventSpace {
         RuntimeState& st = state();
         EventSpaceDev v;
         memset(&v, 0, sizeof(v));
-        v.seg = seg; v.compact = compact; v.seg_start = seg_start;
-        v.slots = slots; v.seg_stride = N + nseg; v.N = N; v.nseg = nseg; v.lag = lag(); v.id = id;
+        v.ids = ids; v.cnt = cnt; v.compact = compact; v.seg_start = seg_start;
+        v.slots = slots; v.N = N; v.nseg = nseg; v.lag = lag(); v.id = id;
         int64_t lo, hi;
         rank_range_host(N, st.rank, st.world, lo, hi);
         v.rank_lo = (int)lo; v.rank_hi = (int)hi;
-        v.done = done;
         for (int q = 0; q < st.world; ++q) {
-            v.peer_seg[q] = (int32_t*)peer_seg[q];
-            v.peer_done[q] = peer_done[q] ? (unsigned long long*)peer_done[q] + st.rank : nullptr;
+            v.peer_ids[q] = (unsigned long long*)peer_ids[q];
+            v.peer_cnt[q] = (int32_t*)peer_cnt[q];
         }
         return v;
     }

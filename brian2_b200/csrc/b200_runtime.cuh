@@ -59,28 +59,34 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
 // ---------------------------------------------------------------------------------------------
 // system-scope flavours (multi-GPU: data and flags cross NVLink into peer memory)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+
+// Tags: every word of a segment names the time step it belongs to (never 0, so a
+// zero-initialised slot is never mistaken for a step): counts carry step_tag << 16, ids id_tag << 32.
+__host__ __device__ __forceinline__ int step_tag(int64_t timestep) {
+    int64_t m = (timestep + 1) % 32767;
+    if (m < 0) m += 32767;
+    return (int)m + 1;
+}
+__host__ __device__ __forceinline__ unsigned long long id_tag(int64_t timestep) {
+    return ((unsigned long long)(unsigned int)(timestep + 1)) << 32;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Grid barrier for the persistent kernel.  Monotonic 64-bit arrival counter (never reset inside
 // a launch); `target` is thread-0 private state.  Thread 0 fences on both sides (the gpu-scope
 // fence also invalidates this SM's L1, so plain loads after the barrier see other CTAs' writes).
-// With several GPUs the arrival fence is system-scope: stores this CTA sent to peer rings are
-// then ordered before whatever CTA 0 publishes after the barrier (see publish_done).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target,
                                              const Ctx& c) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += (unsigned long long)c.gnb;
-        if (c.world > 1) __threadfence_system(); else __threadfence();
+        __threadfence();
         atomicAdd(counter, 1ULL);
         while (ld_acquire_u64(counter) < target) {
         }
@@ -159,8 +165,8 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int x) {
 // space -- no communication with other CTAs (the reference's loop is serial, threshold.cpp:18-31).
 //   mask   bit k of lane l  <=>  element (slice.lo + 32*k + l) fired
 // Called by ALL threads of ALL CTAs.  On several GPUs every store is repeated into each peer's
-// ring (NVLink P2P); the step becomes visible to the peers when CTA 0 publishes `done` after the
-// next grid barrier (publish_done).
+// ring (NVLink P2P); a segment becomes visible to the peers with its count word, which carries
+// the step's tag and is stored last with release semantics at system scope.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter, const Ctx& c,
                                               const EventSpaceDev& es, int64_t timestep) {
@@ -168,7 +174,7 @@ __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const Slice sl = owned_slice(es.N, c);
-    const size_t slot_off = (size_t)ring_index(timestep, es.slots) * (size_t)es.seg_stride;
+    const size_t slot = (size_t)ring_index(timestep, es.slots);
     const int segi = c.rank * c.gnb + c.gbid;
 
     int wtotal = __popcll(mask);
@@ -184,38 +190,31 @@ __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter
         if (w < warp) woff += v;
         ctotal += v;
     }
-    const size_t base = slot_off + (size_t)es.seg_start[segi];
     if (threadIdx.x == 0) {
-        es.seg[slot_off + es.N + segi] = ctotal;
+        const int word = (step_tag(timestep) << 16) | ctotal;
+        const size_t o = slot * (size_t)es.nseg + segi;
+        es.cnt[o] = word;
         for (int q = 0; q < c.world; ++q)
-            if (q != c.rank) es.peer_seg[q][slot_off + es.N + segi] = ctotal;
+            if (q != c.rank) es.peer_cnt[q][o] = word;
     }
     if (wtotal > 0) {
+        const size_t base = slot * (size_t)es.N + (size_t)es.seg_start[segi];
+        const unsigned long long tag = id_tag(timestep);
         int pos = woff;
         for (int k = 0; k < niter; ++k) {
             const bool f = (mask >> k) & 1ULL;
             const unsigned int bal = __ballot_sync(0xffffffffu, f);
             if (f) {
                 const int p = pos + __popc(bal & ((1u << lane) - 1u));
-                const int32_t id = (int32_t)(sl.lo + 32 * (int64_t)k + lane);
-                es.seg[base + p] = id;
+                const unsigned long long w = tag | (unsigned int)(sl.lo + 32 * (int64_t)k + lane);
+                es.ids[base + p] = w;
                 for (int q = 0; q < c.world; ++q)
-                    if (q != c.rank) es.peer_seg[q][base + p] = id;
+                    if (q != c.rank) es.peer_ids[q][base + p] = w;
             }
             pos += __popc(bal);
         }
     }
     __syncthreads();            // the CTA's own segment is now readable by all its threads
-}
-
-// Multi-GPU: after the grid barrier that follows the thresholder (all CTAs' peer stores are
-// fenced at system scope by then), tell every peer that step `timestep` of this rank is complete.
-__device__ __forceinline__ void publish_done(const Ctx& c, const EventSpaceDev& es, int64_t timestep) {
-    if (c.world > 1 && c.gbid == 0 && threadIdx.x == 0) {
-        __threadfence_system();
-        for (int q = 0; q < c.world; ++q)
-            if (q != c.rank) st_release_sys_u64(es.peer_done[q], (unsigned long long)(timestep + 1));
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -224,8 +223,10 @@ __device__ __forceinline__ void publish_done(const Ctx& c, const EventSpaceDev& 
 // build it once).  Global spike number g -> id by a binary search in shared memory.
 // ---------------------------------------------------------------------------------------------
 struct SpikeView {
-    const int32_t* slot;    // seg + slot offset
+    const unsigned long long* ids;   // ids of this slot
     const int32_t* seg_start;
+    unsigned long long tag;  // id_tag of the step
+    int remote_lo, remote_hi;   // segments [remote_lo, remote_hi) are the local rank's (no spinning)
     const int* pref;        // shared: pref[j - seg_lo] = number of spikes in segments [seg_lo, j)
     int seg_lo, nseg;       // segments covered
     int total;
@@ -245,31 +246,18 @@ __device__ __forceinline__ void view_reset() {
     __syncthreads();
 }
 
-// wait until every peer has published step `timestep` of this event space (multi-GPU)
-__device__ __forceinline__ void wait_peers(const Ctx& c, const EventSpaceDev& es, int64_t timestep,
-                                           Control* ctrl) {
-    if (c.world > 1 && timestep >= 0) {
-        if (threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
-            const unsigned long long need = (unsigned long long)(timestep + 1);
-            const long long t0 = clock64();
-            while (ld_acquire_sys_u64(&es.done[threadIdx.x]) < need) {
-                if (clock64() - t0 > 40000000000LL || ld_volatile_s32(&ctrl->error)) {   // ~20 s
-                    ctrl->error = 1;
-                    break;
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t timestep, const Ctx& c,
                                                 bool local_only, Control* ctrl) {
     long long* tagp;
     int* pref = view_storage(&tagp);
     SpikeView v;
-    v.slot = es.seg + (size_t)ring_index(timestep, es.slots) * (size_t)es.seg_stride;
+    const size_t slot = (size_t)ring_index(timestep, es.slots);
+    v.ids = es.ids + slot * (size_t)es.N;
+    const int32_t* cnt = es.cnt + slot * (size_t)es.nseg;
     v.seg_start = es.seg_start;
+    v.tag = id_tag(timestep);
+    v.remote_lo = c.rank * c.gnb;
+    v.remote_hi = v.remote_lo + c.gnb;
     v.pref = pref;
     const bool local = local_only && c.world > 1;
     v.seg_lo = local ? c.rank * c.gnb : 0;
@@ -277,8 +265,10 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
     const long long tag = ((long long)(es.id * 2 + (local ? 1 : 0) + 1) << 44) ^ (timestep + 1);
     __syncthreads();
     if (*tagp != tag) {
-        if (!local) wait_peers(c, es, timestep, ctrl);
-        // block-wide exclusive scan of v.nseg counts (<= kMaxSegments)
+        // block-wide exclusive scan of v.nseg counts (<= kMaxSegments); the count words of the
+        // peers' segments are polled until they carry this step's tag (multi-GPU)
+        const int want = step_tag(timestep);
+        const bool poll = c.world > 1 && !local && timestep >= 0;
         __shared__ int s_wsum[kWarps];
         const int per = (v.nseg + kBlock - 1) / kBlock;
         const int first = (int)threadIdx.x * per;
@@ -287,7 +277,29 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
 #pragma unroll
         for (int k = 0; k < kMaxSegments / kBlock; ++k) {
             const int j = first + k;
-            vals[k] = (k < per && j < v.nseg) ? __ldcg(v.slot + es.N + v.seg_lo + j) : 0;
+            int w = 0;
+            if (k < per && j < v.nseg) {
+                const int* wp = cnt + v.seg_lo + j;
+                if (poll && (v.seg_lo + j) / c.gnb != c.rank) {
+                    // segment of a peer: spin until the word carries this step's tag
+                    const long long t0 = clock64();
+                    while (((w = ld_volatile_s32(wp)) >> 16) != want) {
+                        if (clock64() - t0 > 40000000000LL || ld_volatile_s32(&ctrl->error)) {   // ~20 s
+                            ctrl->error = 1;
+                            w = 0;
+                            break;
+                        }
+                    }
+                    if (c.gbid == c.gnb - 1 && k == 0 && j == (c.rank == 0 ? c.gnb : 0)) {   // one sampled thread
+                        ctrl->poll_cycles += (unsigned long long)(clock64() - t0);
+                        ctrl->polls += 1;
+                    }
+                } else {
+                    w = __ldcg(wp);
+                    if (timestep < 0 || (w >> 16) != want) w = 0;   // slot holds no data of this step
+                }
+            }
+            vals[k] = w & 0xffff;
             mine += vals[k];
         }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -319,6 +331,18 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
     return v;
 }
 
+// id stored at position `off` of segment `seg` (absolute segment index); a peer's word may
+// still be in flight: spin until it carries the step's tag
+__device__ __forceinline__ int32_t view_load(const SpikeView& v, int seg, int off) {
+    const unsigned long long* p = v.ids + v.seg_start[seg] + off;
+    unsigned long long w = ld_volatile_u64(p);
+    if (seg < v.remote_lo || seg >= v.remote_hi) {
+        const long long t0 = clock64();
+        while ((w & 0xffffffff00000000ULL) != v.tag && clock64() - t0 < 40000000000LL) w = ld_volatile_u64(p);
+    }
+    return (int32_t)(unsigned int)w;
+}
+
 // id of spike number g (0 <= g < total) of the view
 __device__ __forceinline__ int32_t view_id(const SpikeView& v, int g) {
     int lo = 0, hi = v.nseg;           // last j with pref[j] <= g
@@ -326,7 +350,7 @@ __device__ __forceinline__ int32_t view_id(const SpikeView& v, int g) {
         const int mid = (lo + hi) >> 1;
         if (v.pref[mid] <= g) lo = mid; else hi = mid;
     }
-    return __ldcg(v.slot + v.seg_start[v.seg_lo + lo] + (g - v.pref[lo]));
+    return view_load(v, v.seg_lo + lo, g - v.pref[lo]);
 }
 
 // number of spikes of the view with id < x (for monitors of subgroups, spikemonitor.cpp:15-33)
@@ -338,8 +362,12 @@ __device__ __forceinline__ int view_count_below(const SpikeView& v, const EventS
         const int mid = (lo + hi) >> 1;
         if (v.seg_start[v.seg_lo + mid] <= x) lo = mid; else hi = mid;
     }
-    const int cnt = v.pref[lo + 1] - v.pref[lo];
-    return v.pref[lo] + lower_bound_i32(v.slot + v.seg_start[v.seg_lo + lo], cnt, x);
+    int a = 0, b = v.pref[lo + 1] - v.pref[lo];     // first position in the segment with id >= x
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (view_load(v, v.seg_lo + lo, mid) < x) a = mid + 1; else b = mid;
+    }
+    return v.pref[lo] + a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,8 +382,7 @@ __device__ __forceinline__ void compact_segments(const EventSpaceDev& es, int64_
     int32_t* out = es.compact + (size_t)ring_index(s, es.slots) * (size_t)(es.N + 1);
     for (int j = c.bid; j < v.nseg; j += c.nb) {
         const int beg = v.pref[j], cnt = v.pref[j + 1] - beg;
-        const int32_t* src = v.slot + v.seg_start[j];
-        for (int k = threadIdx.x; k < cnt; k += kBlock) out[beg + k] = __ldcg(src + k);
+        for (int k = threadIdx.x; k < cnt; k += kBlock) out[beg + k] = view_load(v, j, k);
     }
     if (c.bid == 0 && threadIdx.x == 0) out[es.N] = v.total;
 }

@@ -34,27 +34,29 @@ constexpr int kMaxSegments = kMaxRanks * kBlock;   // spike-list segments of one
 
 // Device view of one event space ("spike ring").  A step's spike list exists in two forms:
 //   * segments: CTA b of rank r writes the ids of ITS neurons that fired (ascending) at
-//     seg[slot][seg_start[r*nb+b] ...] and their number at seg[slot][N + r*nb + b]; the
+//     ids[slot][seg_start[r*nb+b] ...] and their number at cnt[slot][r*nb + b]; the
 //     concatenation in segment order is the ascending `_spikespace` of the reference
-//     (threshold.cpp:24-31).  Produced without any inter-CTA communication; on several GPUs the
-//     same stores also go to every peer's ring over NVLink.
+//     (threshold.cpp:24-31).  Produced without any inter-CTA communication.  Every word carries
+//     the tag of its time step (ids: tag << 32 | id, counts: tag16 << 16 | count), so on several
+//     GPUs the same stores simply also go to every peer's ring over NVLink and a reader spins
+//     on the word it needs until the tag matches -- flag and data travel in one word, no fence
+//     or ordering between stores is required on either side.
 //   * compact: ids [0, count) + count at [N], the reference layout, built `lag` steps later by
 //     `compact_segments` for the consumers that look back in time (synaptic delays).
 struct EventSpaceDev {
-    int32_t* seg;             // [slots][seg_stride]
+    unsigned long long* ids;  // [slots][N]
+    int32_t* cnt;             // [slots][nseg]
     int32_t* compact;         // [slots][N + 1]
     const int32_t* seg_start; // [nseg + 1] first neuron of every segment (absolute id)
     int slots;
-    int seg_stride;           // N + nseg
     int N;
     int nseg;                 // world * nb
     int lag;                  // compaction of step s happens during step s + lag
     int id;                   // index of this event space (tag of the cached view)
     int rank_lo, rank_hi;     // neurons owned by this rank
-    // multi-GPU: peers' rings and the per-rank "steps published" counters (this rank's copy)
-    int32_t* peer_seg[kMaxRanks];
-    unsigned long long* peer_done[kMaxRanks];   // address of done[my_rank] on every peer
-    unsigned long long* done;                   // [kMaxRanks] local: done[q] = steps published by rank q
+    // multi-GPU: the peers' rings (CUDA IPC mapped)
+    unsigned long long* peer_ids[kMaxRanks];
+    int32_t* peer_cnt[kMaxRanks];
 };
 
 // Device view of a synaptic pathway (built by b200_host.h: Pathway::prepare)
@@ -78,6 +80,9 @@ struct Control {
     int steps_done;                 // steps completed by the last launch
     int overflow;                   // a monitor buffer is (nearly) full: host must grow it
     int error;                      // != 0: device-side failure (1: peer wait timed out)
+    unsigned long long poll_cycles; // multi-GPU diagnostics (one sampled thread): cycles spent
+    unsigned long long fence_cycles;//   spinning on peers' ready flags / in the acquire fence
+    unsigned long long polls;       //   number of waits sampled
 };
 
 }  // namespace b200

@@ -92,15 +92,8 @@ _kernel_b200_compact{{es.name}}(const _B200Clocks _clks)
     b200::compact_segments(_A._es{{es.name}}, _clks.{{es.clock}}.timestep, _ctx, _A._ctrl);
 }
 B200_REGISTER_KERNEL(_kernel_b200_compact{{es.name}})
-__global__ void _kernel_b200_publish{{es.name}}(const _B200Clocks _clks)
-{
-    const b200::Ctx _ctx{0, 1, 0, 1, _A._rank, _A._world};
-    b200::publish_done(_ctx, _A._es{{es.name}}, _clks.{{es.clock}}.timestep);
-}
 void _run_b200_compact{{es.name}}()
 {
-    if (b200::state().world > 1)   // the thresholder kernel has completed (stream order)
-        _kernel_b200_publish{{es.name}}<<<1, 32, 0, b200::state().stream>>>(_b200_clocks_now());
     _b200_launch_begin("b200_compact{{es.name}}");
     _kernel_b200_compact{{es.name}}<<<_b200_grid_size(), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now());
     _b200_launch_end("b200_compact{{es.name}}");
@@ -154,9 +147,6 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         {% if item.barrier %}
         b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
         B200_PHASE({{2 * loop.index0}})
-        {% for pub in item.publish %}
-        b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
-        {% endfor %}
         {% elif not loop.first %}
         __syncthreads();
         {% endif %}
@@ -185,9 +175,6 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         {% endfor %}
         b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
         B200_PHASE({{2 * (plan.entries | length)}})
-        {% for pub in plan.tail_publish %}
-        b200::publish_done(_ctx, _A._es{{pub.es}}, _clks.{{pub.clock}}.timestep);
-        {% endfor %}
         if (threadIdx.x == 0) _s_stop = b200::ld_volatile_s32(&_A._ctrl->stop) | b200::ld_volatile_s32(&_A._ctrl->error);
         __syncthreads();
         const int _stop = _s_stop;
@@ -229,6 +216,9 @@ static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
     _b200_launch_end("persistent_{{plan.index}}");
     B200_CUDA(cudaMemcpyAsync(st.control_host, st.control, sizeof(b200::Control), cudaMemcpyDeviceToHost, st.stream));
     B200_CUDA(cudaStreamSynchronize(st.stream));
+    st.poll_cycles += (double)st.control_host->poll_cycles;
+    st.fence_cycles += (double)st.control_host->fence_cycles;
+    st.polls += (double)st.control_host->polls;
     if (st.control_host->error)
         throw std::runtime_error("b200: a peer GPU did not deliver its spikes in time (multi-GPU run aborted)");
     return (long long)st.control_host->steps_done;

@@ -157,6 +157,9 @@ double b200_get_counter(const char* key)
     if (k == "download_seconds") return st.download_seconds;
     if (k == "device_bytes") return (double)st.bytes_allocated;
     if (k == "num_sms") return (double)st.num_sms;
+    if (k == "poll_cycles") return st.poll_cycles;
+    if (k == "fence_cycles") return st.fence_cycles;
+    if (k == "polls") return st.polls;
     if (k == "grid") return st.initialised ? (double)_b200_grid_size() : 0.0;
     if (k == "runs") return (double)Network::_b200_run_log.size();
     if (k.compare(0, 5, "phase") == 0) {   // "phase<i>": cycles CTA 0 spent in phase i (profile_phases)
