@@ -38,7 +38,19 @@ WORKLOADS = {
     "cuba_4k": ("cuba", dict(N=4000, p=0.02), 58.0, 20.0),
     "cuba_256k": ("cuba", dict(N=256000, p=80.0 / 256000), 58.0, 20.0),
     "brunel_100k": ("brunel", dict(N_E=80000, epsilon=0.01, deterministic=True), 33.0, 20.0),
+    # propagation stress (brian2/tests/features/speed.py:263-326 SynapsesOnly): every source spikes
+    # every step, `w += 1.0` per event -> the step is synaptic propagation only (20 B/event)
+    "synapses_only_sparse": ("synapses_only", dict(N=100000, p=0.2, rate_hz=10.0), 0.0, 20.0),
+    "synapses_only_dense": ("synapses_only", dict(N=40000, p=1.0, rate_hz=10.0), 0.0, 20.0),
+    "synapses_only_highrate": ("synapses_only", dict(N=100000, p=0.2, rate_hz=100.0), 0.0, 20.0),
 }
+
+
+def _n_neurons(objs):
+    for key in ("P", "neurons", "H"):
+        if key in objs:
+            return len(objs[key])
+    return 0
 
 
 def _peaks():
@@ -214,7 +226,7 @@ def run_b200(args, rank, world):
         for name, cyc in b.device.phase_profile():
             sys.stderr.write(f"PHASE r{rank} {name:55s} {cyc / total_steps / 1.965e3:8.3f} us/step\n")
     model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
-    n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
+    n_neurons = _n_neurons(objs)
     n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
     return dict(dev_s=dev_s, e2e_s=e2e_s, events=events, timesteps=steps, persistent=persistent,
                 h2d=cnt("h2d_bytes") / n_runs, d2h=cnt("d2h_bytes") / n_runs, launches=cnt("launches"),
@@ -235,8 +247,12 @@ def run_reference(args, sim_steps, warmup, steps, threads, strict=False):
         times = [float(line.split()[1]) for line in f if line.startswith("B200BENCH_RUN")]
     assert len(times) == n_runs, (times, n_runs)
     loop_s = sum(times[warmup:])
-    events, nspikes = _outdegree_events(b, objs, warmup * sim_steps * 1e-4)
-    n_neurons = len(objs["P"]) if "P" in objs else len(objs["neurons"])
+    if "spikes" in objs:
+        events, nspikes = _outdegree_events(b, objs, warmup * sim_steps * 1e-4)
+    else:   # SynapsesOnly: every source spikes every step, so every synapse carries one event per step
+        n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
+        events, nspikes = float(n_syn) * steps * sim_steps, None
+    n_neurons = _n_neurons(objs)
     return dict(loop_s=loop_s, events=events, timesteps=steps * sim_steps, n_neurons=n_neurons,
                 spikes=nspikes)
 

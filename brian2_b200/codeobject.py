@@ -32,6 +32,8 @@ DEVICE_TEMPLATES = {
     "spikemonitor",
     "statemonitor",
     "ratemonitor",
+    "spikegenerator",
+    "summed_variable",
 }
 
 #: templates that only ever run once, on the host, before/between runs
@@ -130,3 +132,62 @@ DEFAULT_FUNCTIONS["randn"].implementations.add_implementation(
     code={"support_code": "", "hashdefine_code": "#define _randn(_i) b200::rng_normal(_rng)"},
     name="_randn",
 )
+
+
+# ---------------------------------------------------------------------------------------------
+# BinomialFunction (PoissonInput): the reference generates one sampler per instance through the
+# class-level table ``BinomialFunction.implementations`` (input/binomial.py:168, applied at
+# :207-220) -- "this container can be extended by other code generation targets".  Device
+# flavour: the same inversion / normal-approximation algorithm (input/binomial.py:85-143, itself
+# numpy's rk_binomial_inversion), drawing from the element's Philox stream `_rng` that the
+# templates create; the call `name(_vectorisation_idx)` is a macro that passes `_rng` along.
+# ---------------------------------------------------------------------------------------------
+def _generate_cuda_binomial(n, p, use_normal, name):
+    from brian2.input.binomial import _pre_calc_constants, _pre_calc_constants_approximated
+
+    if use_normal:
+        loc, scale = _pre_calc_constants_approximated(n, p)
+        # (the C++ target returns `float` here, input/binomial.py:91: same rounding kept)
+        support = f"""
+        __device__ __forceinline__ float {name}_b200(b200::Rng& _rng)
+        {{
+            return b200::rng_normal(_rng) * {scale:.15f} + {loc:.15f};
+        }}
+        """
+    else:
+        reverse, q, P, qn, bound = _pre_calc_constants(n, p)
+        ret = f"{int(n)}-X" if reverse else "X"
+        support = f"""
+        __device__ __forceinline__ long {name}_b200(b200::Rng& _rng)
+        {{
+            long X = 0;
+            double px = {qn:.15f};
+            double U = b200::rng_uniform(_rng);
+            while (U > px)
+            {{
+                X++;
+                if (X > {bound:.15f})
+                {{
+                    X = 0;
+                    px = {qn:.15f};
+                    U = b200::rng_uniform(_rng);
+                }} else
+                {{
+                    U -= px;
+                    px = (({int(n)}-X+1) * {P:.15f} * px)/(X*{q:.15f});
+                }}
+            }}
+            return {ret};
+        }}
+        """
+    code = {"support_code": support, "hashdefine_code": f"#define {name}(_i) {name}_b200(_rng)"}
+    return code, {}
+
+
+def _register_binomial():
+    from brian2.input.binomial import BinomialFunction
+
+    BinomialFunction.implementations["cuda"] = _generate_cuda_binomial
+
+
+_register_binomial()

@@ -455,4 +455,59 @@ public:
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// TargetIndex: CSR by target element for summed variables (summed_variable.cpp:20-27 adds the
+// synapses' values in synapse-index order; a counting sort by target keeps that order per row).
+// ---------------------------------------------------------------------------------------------
+class TargetIndex {
+public:
+    int n_targets = 0;
+    int* d_rowptr = nullptr;
+    int* d_syn_ids = nullptr;
+    bool prepared = false;
+
+    ~TargetIndex() { release(); }
+    void release() {
+        dev_free(d_rowptr); dev_free(d_syn_ids);
+        d_rowptr = d_syn_ids = nullptr;
+    }
+    // index[i]: absolute target element of synapse i; rows cover [target_start, target_start + size)
+    void prepare(const int32_t* index, size_t n_syn, int target_start, int target_size) {
+        runtime_init();
+        release();
+        if (n_syn >= (size_t)INT32_MAX) throw std::runtime_error("b200: more than 2^31-1 synapses");
+        n_targets = target_size;
+        std::vector<int> rowptr((size_t)target_size + 1, 0);
+        size_t kept = 0;
+        for (size_t i = 0; i < n_syn; ++i) {
+            const int t = index[i] - target_start;
+            if (t < 0 || t >= target_size) continue;
+            rowptr[(size_t)t + 1]++;
+            kept++;
+        }
+        for (int t = 0; t < target_size; ++t) rowptr[(size_t)t + 1] += rowptr[t];
+        std::vector<int> syn_ids(kept);
+        {
+            std::vector<int> cursor(rowptr.begin(), rowptr.end() - 1);
+            for (size_t i = 0; i < n_syn; ++i) {
+                const int t = index[i] - target_start;
+                if (t < 0 || t >= target_size) continue;
+                syn_ids[cursor[t]++] = (int)i;
+            }
+        }
+        d_rowptr = (int*)dev_alloc(rowptr.size() * sizeof(int));
+        d_syn_ids = (int*)dev_alloc(std::max<size_t>(1, kept) * sizeof(int));
+        B200_CUDA(cudaMemcpy(d_rowptr, rowptr.data(), rowptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (kept) B200_CUDA(cudaMemcpy(d_syn_ids, syn_ids.data(), kept * sizeof(int), cudaMemcpyHostToDevice));
+        prepared = true;
+    }
+    TargetIndexDev view() const {
+        TargetIndexDev v;
+        v.n_targets = n_targets;
+        v.rowptr = d_rowptr;
+        v.syn_ids = d_syn_ids;
+        return v;
+    }
+};
+
 }  // namespace b200

@@ -47,6 +47,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -78,17 +83,21 @@ __host__ __device__ __forceinline__ unsigned long long id_tag(int64_t timestep) 
 
 // ---------------------------------------------------------------------------------------------
 // Grid barrier for the persistent kernel.  Monotonic 64-bit arrival counter (never reset inside
-// a launch); `target` is thread-0 private state.  Thread 0 fences on both sides (the gpu-scope
-// fence also invalidates this SM's L1, so plain loads after the barrier see other CTAs' writes).
+// a launch); `target` is thread-0 private state.  Release on arrival, acquire fence after the wait
+// (the gpu-scope fence also invalidates this SM's L1, so plain loads after the barrier see other
+// CTAs' writes).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target,
                                              const Ctx& c) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += (unsigned long long)c.gnb;
-        __threadfence();
-        atomicAdd(counter, 1ULL);
-        while (ld_acquire_u64(counter) < target) {
+        // arrive: release-RMW without a return value (the CTA's earlier writes are ordered before
+        // it through the bar.sync above; no round trip to wait for before polling starts)
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ULL) : "memory");
+        // wait: relaxed polls (served by L2, no L1 invalidation per iteration), one acquire
+        // fence at the end -- it also drops this SM's stale L1 lines for the plain loads that follow
+        while (ld_relaxed_u64(counter) < target) {
         }
         __threadfence();
     }
@@ -108,6 +117,7 @@ struct Slice {
 };
 
 __host__ __device__ __forceinline__ void rank_range(int64_t N, int rank, int world, int64_t& lo, int64_t& hi) {
+    if (world == 1) { lo = 0; hi = N; return; }
     int64_t per = (N + world - 1) / world;
     per = (per + 31) & ~(int64_t)31;
     lo = (int64_t)rank * per; if (lo > N) lo = N;
@@ -116,7 +126,11 @@ __host__ __device__ __forceinline__ void rank_range(int64_t N, int rank, int wor
 // first element owned by global warp g (of G) inside the rank range [lo, hi)
 __host__ __device__ __forceinline__ int64_t warp_first(int64_t lo, int64_t hi, int64_t g, int64_t G) {
     const int64_t T = (hi - lo + 31) >> 5;
-    int64_t e = lo + 32 * ((g * T) / G);
+    // (same quotient either way; the 32-bit division is ~10x cheaper on the device and covers
+    // every group of fewer than 2^32 / (32 G) elements per rank)
+    const int64_t q = (T * G < 0xffffffffLL) ? (int64_t)((unsigned int)(g * T) / (unsigned int)G)
+                                              : (g * T) / G;
+    int64_t e = lo + 32 * q;
     return e < hi ? e : hi;
 }
 

@@ -73,6 +73,14 @@ struct PathwayDev {
     unsigned long long* events;   // number of delivered synaptic events (for the metric)
 };
 
+// Device view of a by-target index of a Synapses object (summed variables): row t lists the
+// synapses (ascending index) whose target element is t + target_start
+struct TargetIndexDev {
+    int n_targets;
+    const int* rowptr;        // [n_targets + 1]
+    const int* syn_ids;       // [number of synapses with a target in range]
+};
+
 // Control block shared by host and the persistent kernel
 struct Control {
     unsigned long long barrier;     // grid barrier arrival counter

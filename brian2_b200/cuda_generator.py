@@ -88,6 +88,138 @@ def _annotate_host_device(code):
     return "\n".join(out)
 
 
+class _CallCSE:
+    """Common-subexpression elimination of stateless function calls and powers over the vector
+    statements of one block.
+
+    The state-update code Brian generates repeats whole sub-expressions textually (the
+    exponential-Euler form ``_BA_x = B/A; _x = -_BA_x + (_BA_x + x)*exp(dt*A)`` contains ``A``
+    twice) and the reference leaves the clean-up to the C++ compiler.  nvcc
+    merges pure arithmetic, but not calls whose inlined body has control flow (``_exprel``:
+    early returns around ``expm1(x)/x``; the double-double integer power; ``exp``/``expm1``
+    with their range checks) -- on COBAHH these re-evaluations were half of all executed
+    instructions.  Evaluating an identical expression once cannot change a single bit of the
+    result, so it is done here, on the abstract code: value numbering over every ``float``
+    valued stateless call / power; expressions seen more than once while their inputs are
+    unchanged become ``_cse_k`` temporaries, the others are put back in place."""
+
+    def __init__(self, variables, float_dtype, keep_exp_pow=True):
+        from brian2.parsing.rendering import NodeRenderer
+
+        self.variables = variables
+        self.float_dtype = float_dtype
+        self.keep_exp_pow = keep_exp_pow
+        self.render = NodeRenderer().render_node
+
+    @staticmethod
+    def _is_exp_pow(node):
+        import ast
+
+        return (isinstance(node, ast.BinOp) and isinstance(node.op, ast.Pow)
+                and isinstance(node.left, ast.Call) and getattr(node.left.func, "id", None) == "exp"
+                and len(node.left.args) == 1)
+
+    @staticmethod
+    def _is_candidate(node):
+        import ast
+
+        if getattr(node, "dtype", None) != "float" or not getattr(node, "stateless", False):
+            return False
+        if getattr(node, "scalar", False):
+            return False
+        if isinstance(node, ast.Call):
+            return True
+        return isinstance(node, ast.BinOp) and isinstance(node.op, ast.Pow)
+
+    def run(self, statements):
+        import ast
+
+        from brian2.parsing.bast import brian_ast
+
+        available = {}      # canonical text -> temporary
+        definition = {}     # temporary -> canonical text (in terms of variables and older temporaries)
+        uses = {}           # temporary -> number of references
+        deps = {}           # temporary -> base identifiers it is computed from
+        order = []          # (position in `out`, temporary)
+        out = []
+        outer = self
+
+        class Numbering(ast.NodeTransformer):
+            def visit(self, node):
+                if outer.keep_exp_pow and outer._is_exp_pow(node) and outer._is_candidate(node):
+                    # `exp(a)**c` is ONE operation on the device (_b200_exp_pow): number the
+                    # argument's sub-terms, never the inner exp() on its own
+                    node.left.args[0] = self.visit(node.left.args[0])
+                    node.right = self.visit(node.right)
+                    return self._number(node)
+                node = self.generic_visit(node)
+                if outer._is_candidate(node):
+                    return self._number(node)
+                return node
+
+            def _number(self, node):
+                key = outer.render(node)
+                name = available.get(key)
+                if name is None:
+                    name = f"_cse_{len(definition)}"
+                    available[key] = name
+                    definition[name] = key
+                    uses[name] = 0
+                    d = set()
+                    for ident in get_identifiers(key):
+                        d |= deps.get(ident, {ident})
+                    deps[name] = d
+                    pending.append(name)
+                uses[name] += 1
+                return ast.copy_location(ast.Name(id=name, ctx=ast.Load()), node)
+
+        for stmt in statements:
+            pending = []
+            new_expr = None
+            if not stmt.used_boolean_variables:
+                try:
+                    tree = Numbering().visit(brian_ast(str(stmt.expr), self.variables))
+                    new_expr = self.render(tree)
+                except Exception:
+                    return statements          # anything unusual: leave the block alone
+            for name in pending:
+                order.append(name)
+                out.append(("temp", name))
+            out.append(("stmt", stmt, new_expr))
+            # a write to `stmt.var` invalidates every temporary computed from it
+            for key in [k for k, name in available.items() if stmt.var in deps[name]]:
+                del available[key]
+
+        if not any(n > 1 for n in uses.values()):
+            return statements
+        # single-use temporaries go back where they came from (newest first, so that nested
+        # single-use terms unfold completely)
+        inline = {}
+        for name in reversed(order):
+            if uses[name] == 1:
+                inline[name] = f"({word_substitute(definition[name], inline)})"
+        result = []
+        for item in out:
+            if item[0] == "temp":
+                name = item[1]
+                if name in inline:
+                    continue
+                result.append(Statement(name, ":=", word_substitute(definition[name], inline), "",
+                                        self.float_dtype, constant=True))
+            else:
+                _, stmt, new_expr = item
+                if new_expr is None:
+                    result.append(stmt)
+                    continue
+                new = Statement(stmt.var, stmt.op, word_substitute(new_expr, inline), stmt.comment,
+                                stmt.dtype, constant=stmt.constant, subexpression=stmt.subexpression,
+                                scalar=stmt.scalar)
+                new.used_boolean_variables = stmt.used_boolean_variables
+                new.boolean_simplified_expressions = stmt.boolean_simplified_expressions
+                result.append(new)
+        return result
+
+
 class CUDANodeRenderer(CPPNodeRenderer):
     """C++ expression renderer with one device-specific rewrite: ``exp(a)**c`` becomes
     ``_b200_exp_pow(a, c)`` (csrc/b200_functions.cuh) -- see there for the numerics."""
@@ -152,7 +284,14 @@ class CUDACodeGenerator(CPPCodeGenerator):
         if isinstance(var, Constant):
             return True
         if isinstance(var, Function):
-            return bool(getattr(var, "stateless", True))
+            if not getattr(var, "stateless", True):
+                return False
+            # functions that read arrays from their namespace (TimedArray) are evaluated on the
+            # device, where those arrays live
+            try:
+                return not self._function_namespace_arrays(var)
+            except KeyError:
+                return True
         if isinstance(var, ArrayVariable):
             if not (var.scalar or self.variable_indices[name] == "0"):
                 return False
@@ -256,6 +395,11 @@ class CUDACodeGenerator(CPPCodeGenerator):
         for block_name in sc_statements:
             sc_block = sc_statements[block_name]
             ve_block = ve_statements[block_name]
+            if prefs["devices.b200.cse"]:
+                ve_block = _CallCSE(
+                    self.variables, prefs["core.default_float_dtype"],
+                    keep_exp_pow=bool(prefs["devices.b200.fuse_exp_pow"]),
+                ).run(ve_block)
             sc_read, sc_write, sc_indices, sc_cond = self.arrays_helper(sc_block)
             ve_read, ve_write, ve_indices, ve_cond = self.arrays_helper(ve_block)
             # scalar variables needed by the vector code are read once, in the scalar block
@@ -368,8 +512,22 @@ class CUDACodeGenerator(CPPCodeGenerator):
                 if user_func is not None:
                     hd, ps, sc, uf = user_func
                     user_functions.extend(uf)
+                    # Arrays in a function's namespace (e.g. the values of a TimedArray): the C++
+                    # target keeps them in file-scope statics assigned inside the code object
+                    # (cpp_generator.py:459-474).  Device code reads them through the array
+                    # table instead: `_namespace<key>` becomes a macro for `_A.<key>` and the
+                    # device registers <key> for upload next to the ordinary arrays.
+                    ns_keys = self._function_namespace_arrays(variable)
+                    for key, (ctype, size) in ns_keys.items():
+                        self.device._b200_func_arrays[key] = (ctype, size)
+                        support_code.append(f"#define _namespace{key} (_A.{key})")
                     for code in sc:
+                        if any(code.strip() == f"static {ctype}* _namespace{key};"
+                               for key, (ctype, _) in ns_keys.items()):
+                            continue
                         support_code.append(self._device_support_code(code))
+                    ps = [line for line in ps
+                          if not any(line.strip().startswith(f"_namespace{key} =") for key in ns_keys)]
                     pointers.extend(ps)
                     host_pointers.extend(ps)
                     hash_defines.extend(hd)
@@ -382,6 +540,23 @@ class CUDACodeGenerator(CPPCodeGenerator):
             "denormals_code_lines": [],
             "b200_uses_rng": uses_rng,
         }
+
+    def _function_namespace_arrays(self, variable, seen=None):
+        """{namespace key: (ctype, size)} of the arrays a function (and its dependencies) brings
+        along in its namespace."""
+        seen = seen if seen is not None else set()
+        out = {}
+        if variable in seen:
+            return out
+        seen.add(variable)
+        impl = variable.implementations[self.codeobj_class]
+        for key, value in (impl.get_namespace(self.owner) or {}).items():
+            if hasattr(value, "dtype") and getattr(value, "shape", ()) != ():
+                out[key] = (self.c_data_type(value.dtype), int(value.size))
+        for dep in (impl.dependencies or {}).values():
+            if isinstance(dep, Function):
+                out.update(self._function_namespace_arrays(dep, seen))
+        return out
 
     def _device_support_code(self, code):
         code = deindent(code)

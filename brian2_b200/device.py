@@ -46,6 +46,9 @@ from .cuda_generator import clock_field, is_eventspace
 
 __all__ = ["B200Device", "b200_device"]
 
+#: templates that write a step's spike list into the spike ring (segments of the owning CTAs)
+SPIKE_SOURCE_TEMPLATES = ("threshold", "spikegenerator")
+
 logger = get_logger("brian2.devices.b200")
 
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -108,6 +111,13 @@ prefs.register_preferences(
         (the reference's glibc result is, too); the fused form costs a third.
         """,
     ),
+    cse=BrianPreference(
+        default=True,
+        docs="""
+        Evaluate repeated stateless function calls / powers of the vector code once (value
+        numbering on the abstract code, see `brian2_b200.cuda_generator._CallCSE`).  Bit-neutral.
+        """,
+    ),
     split_phases=BrianPreference(
         default=True,
         docs="""
@@ -158,6 +168,8 @@ class B200Device(CPPStandaloneDevice):
         #: out-of-band communicator of a multi-GPU run (brian2_b200.multigpu.Communicator)
         self._b200_comm = getattr(self, "_b200_comm", None)
         self._b200_written_vars = set()
+        #: arrays from function namespaces (TimedArray values ...): name -> (ctype, size)
+        self._b200_func_arrays = {}
         self.cu_source_files = []
 
     # ------------------------------------------------------------------------------------------
@@ -206,6 +218,12 @@ class B200Device(CPPStandaloneDevice):
                 post_group = owner.synapses.target
                 post_parent = getattr(post_group, "source", post_group)
                 template_kwds["b200_post_parent_size"] = int(len(post_parent))
+            if template_name == "spikegenerator":
+                template_kwds["eventspace_variable"] = owner.variables["_spikespace"]
+            if template_name == "summed_variable":
+                from brian2.groups.neurongroup import NeuronGroup
+
+                template_kwds["b200_target_whole_group"] = isinstance(owner.target, NeuronGroup)
             if template_name == "statemonitor":
                 from brian2.groups.neurongroup import NeuronGroup
 
@@ -302,7 +320,7 @@ class B200Device(CPPStandaloneDevice):
                 clock = clocks_by_name[m.group(1)]
                 entries.append((clock, codeobj))
                 info = self._b200_info.get(codeobj.name)
-                if info is not None and info["template"] == "threshold":
+                if info is not None and info["template"] in SPIKE_SOURCE_TEMPLATES:
                     es = info["template_kwds"]["eventspace_variable"]
                     compactions.append((clock, self.get_array_name(es, access_data=False)))
         # Only order-dependent (serial) synaptic code reads the compacted list of the CURRENT
@@ -328,7 +346,7 @@ class B200Device(CPPStandaloneDevice):
             line = f"{net.name}.add(&{clock.name}, _run_b200_compact{es_name});"
             if needs_early(es_name):
                 pos = next(k for k, (_, co) in enumerate(entries)
-                           if not isinstance(co, tuple) and self._b200_info.get(co.name, {}).get("template") == "threshold"
+                           if not isinstance(co, tuple) and self._b200_info.get(co.name, {}).get("template") in SPIKE_SOURCE_TEMPLATES
                            and self.get_array_name(self._b200_info[co.name]["template_kwds"]["eventspace_variable"],
                                                    access_data=False) == es_name)
                 entries.insert(pos + 1, item)
@@ -379,7 +397,7 @@ class B200Device(CPPStandaloneDevice):
         for varname in tmpl.writes_read_only:
             if varname in codeobj.variables and isinstance(codeobj.variables[varname], ArrayVariable):
                 shared_w.add(name_of(codeobj.variables[varname]))
-        if template == "threshold":
+        if template in SPIKE_SOURCE_TEMPLATES:
             # the CTA's own segment of the event space: other CTAs read it -> shared write
             shared_w.add(name_of(es))
             if kw.get("_uses_refractory"):
@@ -397,6 +415,15 @@ class B200Device(CPPStandaloneDevice):
                 shared_r.add(name_of(es) + "__compact")
         elif template == "ratemonitor":
             shared_r.add(name_of(codeobj.variables["_spikespace"]))
+        elif template == "summed_variable":
+            # gather by target element: all reads are "somebody else's" elements; the target
+            # itself is written by its owner when the target is a whole group
+            shared_r |= priv_r
+            priv_r = set()
+            target = name_of(kw["_target_var"])
+            shared_w.discard(target)
+            priv_w.discard(target)
+            (priv_w if kw.get("b200_target_whole_group") else shared_w).add(target)
         if template in ("spikemonitor", "statemonitor", "ratemonitor"):
             for var in self._monitor_buffers(codeobj):
                 shared_w.add(name_of(var))
@@ -453,7 +480,7 @@ class B200Device(CPPStandaloneDevice):
             pr, pw, sr, sw = self._codeobj_access(codeobj)
             add(codeobj.name, "codeobj", pr, pw, sr, sw, owned=self._is_owned_type(codeobj),
                 extra={"weight": 6 if info["template"] == "synapses" else 1})
-            if info["template"] == "threshold":
+            if info["template"] in SPIKE_SOURCE_TEMPLATES:
                 es = info["template_kwds"]["eventspace_variable"]
                 ph_thresholders.append(
                     {"es": self.get_array_name(es, access_data=False), "clock": es.owner.clock.name}
@@ -483,7 +510,9 @@ class B200Device(CPPStandaloneDevice):
 
     def _is_owned_type(self, codeobj):
         info = self._b200_info[codeobj.name]
-        return info["template"] in ("stateupdate", "threshold", "reset") or (
+        if info["template"] == "summed_variable":
+            return bool(info["template_kwds"].get("b200_target_whole_group"))
+        return info["template"] in ("stateupdate", "threshold", "reset", "spikegenerator") or (
             info["template"] == "statemonitor" and info["template_kwds"].get("b200_source_size") is not None
         )
 
@@ -614,6 +643,15 @@ class B200Device(CPPStandaloneDevice):
                 if clock_field(var) is not None:
                     entry["used"] = False   # clocks travel by value
             table.append(entry)
+        # read-only arrays of function namespaces (host side: the reference's static arrays,
+        # devices/cpp_standalone/device.py:1094-1116)
+        for name, (ctype, size) in sorted(self._b200_func_arrays.items()):
+            table.append({
+                "name": name, "ctype": ctype, "used": True, "written": False,
+                "user_name": f"_function.{name}", "monitor": None, "min_cap": 0,
+                "eventspace": False, "clock": None, "width": 1, "dyn_name": None,
+                "size": size, "kind": "static",
+            })
         return table
 
     def _eventspaces(self):
@@ -629,6 +667,15 @@ class B200Device(CPPStandaloneDevice):
                         "clock": var.owner.clock.name,
                     }
         return [spaces[k] for k in sorted(spaces)]
+
+    def _summed_updaters(self):
+        """Names of the SummedVariableUpdater objects (one by-target index each)."""
+        names = set()
+        for codeobj in self.code_objects.values():
+            info = self._b200_info.get(codeobj.name)
+            if info is not None and info["template"] == "summed_variable":
+                names.add(f'{info["owner"].name}_{info["template_kwds"]["_target_var"].name}')
+        return sorted(names)
 
     def _pathways(self, synapses):
         out = []
@@ -677,6 +724,7 @@ class B200Device(CPPStandaloneDevice):
             b200_eventspaces=self._eventspaces(),
             b200_pathways=self._pathways(synapses),
             b200_monitors=monitors,
+            b200_summed=self._summed_updaters(),
         )
         writer.write("b200_objects.h", dev_tmp.h_file)
         writer.write("b200_objects.cpp", dev_tmp.cpp_file)
@@ -909,6 +957,8 @@ class B200Device(CPPStandaloneDevice):
             if info is None:
                 continue
             template, owner = info["template"], info["owner"]
+            if template == "summed_variable":
+                raise NotImplementedError("b200 multi-GPU: summed variables")
             if template == "stateupdate" and isinstance(owner, Synapses):
                 raise NotImplementedError("b200 multi-GPU: clock-driven synaptic equations")
             if template == "statemonitor" and info["template_kwds"].get("b200_source_size") is None:

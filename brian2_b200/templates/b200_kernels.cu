@@ -84,7 +84,7 @@ int _b200_grid_size()
 
 // ---- implicit companions of the thresholders: compaction of an event space (stepwise mode) ----
 {% for es in b200_eventspaces %}
-__global__ void __launch_bounds__(b200::kBlock)
+__global__ void __launch_bounds__(b200::kBlock, {{ctas_per_sm}})
 _kernel_b200_compact{{es.name}}(const _B200Clocks _clks)
 {
     const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
@@ -124,7 +124,7 @@ struct _B200Scal_{{plan.index}} {
     int _unused;
 };
 
-__global__ void __launch_bounds__(b200::kBlock)
+__global__ void __launch_bounds__(b200::kBlock, {{ctas_per_sm}})
 _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
 {
     const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
@@ -141,7 +141,9 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     {% endif %}
     while (_step < _nsteps)
     {
-        if (_ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
+        // the stop flag lives in host memory (one PCIe round trip per poll): look at it every
+        // 64 steps only -- a stop request is honoured within a few milliseconds
+        if ((_step & 63) == 0 && _ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
             _A._ctrl->stop = 1;
         {% for item in plan.entries %}
         {% if item.barrier %}

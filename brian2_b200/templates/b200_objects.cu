@@ -37,6 +37,9 @@ struct _B200Arrays {
     {% for mon in b200_monitors %}
     long long* _monN_{{mon.name}};
     {% endfor %}
+    {% for sv in b200_summed %}
+    b200::TargetIndexDev _sv_{{sv}};
+    {% endfor %}
 };
 
 extern _B200Arrays _A_host;
@@ -48,6 +51,9 @@ namespace brian {
 extern b200::Pathway {{pw.name}};
 {% endfor %}
 }
+{% for sv in b200_summed %}
+extern b200::TargetIndex _b200_sv_{{sv}};
+{% endfor %}
 
 {% for es in b200_eventspaces %}
 void _run_b200_compact{{es.name}}();   // implicit companion of the thresholder (stepwise mode)
@@ -85,6 +91,9 @@ namespace brian {
 b200::Pathway {{pw.name}}({{pw.sources}}, {{pw.start}}, {{pw.stop}});
 {% endfor %}
 }
+{% for sv in b200_summed %}
+b200::TargetIndex _b200_sv_{{sv}};
+{% endfor %}
 
 // per-monitor host bookkeeping: upper bound of the number of recorded entries
 {% for mon in b200_monitors %}
@@ -168,6 +177,10 @@ void _b200_upload()
     {% for pw in b200_pathways %}
     if (brian::{{pw.name}}.prepared)
         _A_host._pw_{{pw.name}} = brian::{{pw.name}}.view();
+    {% endfor %}
+    {% for sv in b200_summed %}
+    if (_b200_sv_{{sv}}.prepared)
+        _A_host._sv_{{sv}} = _b200_sv_{{sv}}.view();
     {% endfor %}
     {% for mon in b200_monitors %}
     {

@@ -45,7 +45,7 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}(const b200::Ctx& _ctx, con
     {% endblock %}
 }
 
-__global__ void __launch_bounds__(b200::kBlock)
+__global__ void __launch_bounds__(b200::kBlock, {{prefs.devices.b200.ctas_per_sm}})
 _kernel_{{codeobj_name}}(const _B200Clocks _clks, const _co_{{codeobj_name}}::Scal _sc)
 {
     const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};

@@ -19,11 +19,20 @@
     }
     // scalar code
     {{scalar_code|autoindent}}
+    {% if b200_source_size is not none %}
     const b200::Slice _mine = b200::owned_cta((int64_t){{b200_source_size}}, _ctx);
     for (int _i = threadIdx.x; _i < (int)_num_indices; _i += b200::kBlock)
     {
         const int _idx = {{_indices}}[_i];
         if (_idx < _mine.lo || _idx >= _mine.hi) continue;
+    {% else %}
+    {# source is not a whole NeuronGroup (synapses, subgroup): no element ownership to exploit;
+       the recorded entries are spread over the CTAs and the barrier analysis treats the reads as
+       shared #}
+    for (int _i = _ctx.bid * b200::kBlock + threadIdx.x; _i < (int)_num_indices; _i += _ctx.nb * b200::kBlock)
+    {
+        const int _idx = {{_indices}}[_i];
+    {% endif %}
         const int _vectorisation_idx = _idx;
         {{vector_code|autoindent}}
         {% for varname, var in _recorded_variables | dictsort %}

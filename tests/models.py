@@ -130,8 +130,7 @@ def brunel(b, N_E=800, gamma=0.25, epsilon=0.1, duration=0.1, seed=4321, hetero_
         inh.delay = D
     objs = dict(neurons=neurons, exc=exc, inh=inh)
     if not deterministic:
-        objs["drive"] = b.PoissonInput(target=neurons, target_var="v", N=C_ext, rate=nu_ext, weight=J,
-                                       name="brunel_drive")
+        objs["drive"] = b.PoissonInput(target=neurons, target_var="v", N=C_ext, rate=nu_ext, weight=J)
     if monitor:
         objs["spikes"] = b.SpikeMonitor(neurons, name="brunel_spikes")
         objs["rate"] = b.PopulationRateMonitor(neurons, name="brunel_rate")
@@ -207,7 +206,100 @@ def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, dela
     return objs
 
 
-MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=synapses_only)
+def spikegen(b, N=200, n_spikes=3000, duration=0.05, seed=5, raster_seed=3, period_ms=None):
+    """SpikeGeneratorGroup (templates/spikegenerator.cpp) driving LIF neurons through synapses
+    with heterogeneous delays; `w` is a per-synapse counter changed by on_pre and recorded with
+    a StateMonitor of the Synapses.  All increments are exactly representable, so every sum is
+    exact in any order."""
+    b.seed(seed)
+    ms = b.ms
+    rng = np.random.RandomState(raster_seed)
+    horizon = int(round((period_ms if period_ms else duration * 1e3) * 10))   # time bins
+    # at most one spike per neuron per bin; spike times are exact bin centres
+    pairs = rng.choice(N * horizon, size=min(n_spikes, N * horizon), replace=False)
+    idx = (pairs % N).astype(np.int32)
+    bins = (pairs // N).astype(np.int64)
+    kwds = dict(period=period_ms * ms) if period_ms else {}
+    SG = b.SpikeGeneratorGroup(N, idx, bins * 0.1 * ms, name="sg_source", **kwds)
+    G = b.NeuronGroup(N, "dv/dt = -v/(10*ms) : 1 (unless refractory)", threshold="v > 1", reset="v = 0",
+                      refractory=2 * ms, method="exact", name="sg_neurons")
+    S = b.Synapses(SG, G, "w : 1", on_pre="v_post += 0.25\nw += 0.125", name="sg_S")
+    S.connect(p=0.05)
+    S.delay = "(int(rand()*5)) * 0.1*ms"
+    objs = dict(SG=SG, G=G, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="sg_spikes")
+    objs["in_spikes"] = b.SpikeMonitor(SG, name="sg_in_spikes")
+    objs["wtrace"] = b.StateMonitor(S, "w", record=[0, 7, 100], name="sg_wtrace")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("S", "w")]
+    return objs
+
+
+def gapjunction(b, N=300, p=0.1, duration=0.05, seed=21):
+    """Summed variable (templates/summed_variable.cpp): electrical coupling
+    `Igap_post = w*(v_pre - v_post) : 1 (summed)` between LIF neurons."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """dv/dt = (I0 - v + Igap)/(10*ms) : 1
+                            I0 : 1
+                            Igap : 1""", threshold="v > 1", reset="v = 0", method="euler", name="gj_neurons")
+    G.v = "rand()"
+    G.I0 = "0.8 + 0.6*rand()"
+    S = b.Synapses(G, G, """w : 1
+                            Igap_post = w*(v_pre - v_post) : 1 (summed)""", name="gj_S")
+    S.connect(condition="i != j", p=p)
+    S.w = "0.02*rand()"
+    objs = dict(G=G, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="gj_spikes")
+    objs["trace"] = b.StateMonitor(G, "Igap", record=[0, 1, N - 1], name="gj_trace")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("G", "Igap")]
+    return objs
+
+
+def timedarray(b, N=100, duration=0.05, seed=8):
+    """2-d TimedArray stimulus (input/timedarray.py:282-345) read inside the state update."""
+    b.seed(seed)
+    ms = b.ms
+    rng = np.random.RandomState(seed)
+    stim = b.TimedArray(rng.uniform(0.5, 2.0, size=(25, 4)), dt=2 * ms, name="ta_stim")
+    G = b.NeuronGroup(N, "dv/dt = (ta_stim(t, i % 4) - v)/(10*ms) : 1", threshold="v > 1", reset="v = 0",
+                      method="euler", name="ta_neurons", namespace=dict(ta_stim=stim))
+    G.v = "rand()"
+    objs = dict(G=G)
+    objs["spikes"] = b.SpikeMonitor(G, name="ta_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v")]
+    return objs
+
+
+def poisson_drive(b, N=2000, duration=0.1, seed=31):
+    """In-loop random numbers: PoissonInput (binomial sampler) + PoissonGroup thresholder feeding LIF
+    neurons.  No cross-target reproducibility (docs_sphinx/advanced/random.rst:28-39): compared
+    statistically."""
+    b.seed(seed)
+    ms, Hz = b.ms, b.Hz
+    G = b.NeuronGroup(N, "dv/dt = -v/(10*ms) : 1", threshold="v > 1", reset="v = 0", method="exact",
+                      name="pd_neurons")
+    PI = b.PoissonInput(G, "v", N=200, rate=20 * Hz, weight=0.03)
+    PG = b.PoissonGroup(500, rates=40 * Hz, name="pd_group")
+    S = b.Synapses(PG, G, on_pre="v += 0.05", name="pd_S")
+    S.connect(p=0.02)
+    objs = dict(G=G, PI=PI, PG=PG, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="pd_spikes")
+    objs["in_spikes"] = b.SpikeMonitor(PG, name="pd_in_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v")]
+    return objs
+
+
+MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=synapses_only,
+              spikegen=spikegen, gapjunction=gapjunction, timedarray=timedarray,
+              poisson_drive=poisson_drive)
 
 
 def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):

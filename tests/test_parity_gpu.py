@@ -41,6 +41,12 @@ def _check(case, res, exact_state):
     ("cobahh_1000", False),
     # per-synapse weights are accumulated with fp64 atomics (order not deterministic)
     ("stdp_1000", False),
+    # next rows of SURVEY.md 8(a10/f): SpikeGeneratorGroup (+ StateMonitor of synapses), summed
+    # variables (gathered in the reference's summation order), TimedArray
+    ("spikegen", True),
+    ("spikegen_period", True),
+    ("gapjunction", True),
+    ("timedarray", True),
 ])
 def test_spike_exact_persistent(brian, project_dir, case, exact_state):
     model, kwds = CASES[case]
@@ -56,6 +62,23 @@ def test_spike_exact_stepwise(brian, project_dir, case):
                                  prefs_update={"devices.b200.persistent": False}, **kwds)
     _check(case, res, True)
     brian.prefs["devices.b200.persistent"] = True
+
+
+def test_in_loop_random_numbers_statistics(brian, project_dir):
+    """PoissonInput (binomial sampler) + PoissonGroup on the device's Philox streams: the reference
+    disclaims cross-target reproducibility of random numbers (docs_sphinx/advanced/random.rst:28-39),
+    so the comparison with its cpp_standalone run is statistical: total spike counts of the driven
+    population and of the PoissonGroup within 5 standard deviations of a Poisson count."""
+    model, kwds = CASES["poisson_drive"]
+    objs, res = models.run_model(brian, model, "b200", project_dir, **kwds)
+    gold = np.load(os.path.join(GOLDEN, "poisson_drive.npz"))
+    for key in ("in_spikes_count", "spikes_count"):
+        g, r = float(gold[key].sum()), float(res[key].sum())
+        assert abs(g - r) < 5.0 * np.sqrt(2.0 * g) + 1, (key, g, r)
+    # the input is not degenerate: per-neuron counts differ between neurons and between seeds
+    assert res["in_spikes_count"].std() > 0
+    assert not np.array_equal(res["in_spikes_count"], gold["in_spikes_count"])
+    np.testing.assert_allclose(res["G_v"].mean(), gold["G_v"].mean(), rtol=0.1)
 
 
 def _gpu_count():
