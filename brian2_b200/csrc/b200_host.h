@@ -415,11 +415,19 @@ public:
             if (syn_ids[k] != (int)k) identity = false;
             csr_target[k] = targets ? targets[syn_ids[k]] : 0;
         }
-        d_bin_delay = (int*)dev_alloc(std::max<size_t>(1, nbins) * sizeof(int));
+        // longest row of every bin: the propagation kernel cuts rows into chunks of equal length
+        std::vector<int> bin_info(bin_delay.begin(), bin_delay.end());
+        for (int b = 0; b < nbins; ++b) {
+            int mx = 0;
+            const int* rp = rowptr.data() + (size_t)b * (nsrc + 1);
+            for (int s = 0; s < nsrc; ++s) mx = std::max(mx, rp[s + 1] - rp[s]);
+            bin_info.push_back(mx);
+        }
+        d_bin_delay = (int*)dev_alloc(std::max<size_t>(1, 2 * nbins) * sizeof(int));
         d_rowptr = (int*)dev_alloc((nrows + 1) * sizeof(int));
         d_syn_ids = (int*)dev_alloc(std::max<size_t>(1, n_owned) * sizeof(int));
         d_csr_target = (int*)dev_alloc(std::max<size_t>(1, n_owned) * sizeof(int));
-        if (nbins) B200_CUDA(cudaMemcpy(d_bin_delay, bin_delay.data(), nbins * sizeof(int), cudaMemcpyHostToDevice));
+        if (nbins) B200_CUDA(cudaMemcpy(d_bin_delay, bin_info.data(), 2 * nbins * sizeof(int), cudaMemcpyHostToDevice));
         B200_CUDA(cudaMemcpy(d_rowptr, rowptr.data(), (nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
         if (n_owned) {
             B200_CUDA(cudaMemcpy(d_syn_ids, syn_ids.data(), n_owned * sizeof(int), cudaMemcpyHostToDevice));
@@ -440,6 +448,7 @@ public:
         v.nbins = nbins;
         v.identity = identity ? 1 : 0;
         v.bin_delay = d_bin_delay;
+        v.bin_maxlen = d_bin_delay + nbins;
         v.rowptr = d_rowptr;
         v.syn_ids = d_syn_ids;
         v.csr_target = d_csr_target;

@@ -66,6 +66,7 @@ struct PathwayDev {
     int nbins;                // distinct integer delays
     int identity;             // 1: csr slot k == synapse index k (no indirection needed)
     const int* bin_delay;     // [nbins] delay in steps, ascending
+    const int* bin_maxlen;    // [nbins] length of the longest row of the bin
     const int* rowptr;        // [nbins*(nsrc+1)+1] slot offsets
     const int* syn_ids;       // [S] synapse index per slot (sorted by delay, source, index)
     const int* csr_target;    // [S] the non-source end of the synapse, packed in slot order

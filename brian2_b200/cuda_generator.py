@@ -335,9 +335,24 @@ class CUDACodeGenerator(CPPCodeGenerator):
             s.var for s in statements if s.var in nonmain_written and s.inplace
         }
         lines = []
+        # pure scatter (`x_post += c`): the delivery loop handles several 32-synapse lines per
+        # iteration, all their index loads issued ahead of the reductions (see synapses.cu)
+        self._b200_unroll = 4 if statements and all(s.var in inplace_targets for s in statements) else 1
         # reads (index arrays first); in-place atomic targets are never loaded
         load_read = set(read) - inplace_targets
         lines += self.translate_to_read_arrays(load_read, write, indices)
+        # The two ends of a synapse are known to the delivery loop without touching
+        # `_synaptic_pre/_post[_idx]`: the spiking neuron is the CSR row, the other end comes from
+        # the pathway's packed `csr_target` stream that the template loads ahead of the body.
+        pathway = getattr(self.device, "_b200_current_template_kwds", {}).get("pathway")
+        prepost = getattr(pathway, "prepost", None)
+        if prepost in ("pre", "post"):
+            ends = {"_presynaptic_idx": "_b200_src_idx" if prepost == "pre" else "_b200_tgt_idx",
+                    "_postsynaptic_idx": "_b200_tgt_idx" if prepost == "pre" else "_b200_src_idx"}
+            for n, line in enumerate(lines):
+                m = re.match(r"^const int32_t (_presynaptic_idx|_postsynaptic_idx) = \w+\[_idx\];$", line)
+                if m:
+                    lines[n] = f"const int32_t {m.group(1)} = {ends[m.group(1)]};"
         lines += self.translate_to_declarations(load_read | inplace_targets, write, indices)
         tmp_count = 0
         for stmt in statements:
@@ -456,6 +471,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
         kwds["b200_scalar_host"] = scal_host
         kwds["b200_scalar_members"] = scal_members
         kwds["b200_serial"] = serial
+        kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)
         # remembered by the device for the barrier analysis of the persistent kernel
         access["serial"] = serial
         self.device._b200_access[self.name] = access
@@ -479,6 +495,10 @@ class CUDACodeGenerator(CPPCodeGenerator):
                 f"const {ctype}* {pointer_name} = b200::compact_slot(_A._es{array_name}, "
                 f"_clks.{clk}.timestep);"
             )
+        if var.constant and var.read_only and not var.scalar:
+            # never written inside a run (e.g. `_synaptic_pre/_post`, synapses.py:1386-1391):
+            # non-coherent loads are safe and the compiler may batch them ahead of the atomics
+            return f"const {ctype}* __restrict__ {pointer_name} = _A.{array_name};"
         return f"{ctype}* {self.restrict}{pointer_name} = _A.{array_name};"
 
     def _host_pointer_line(self, var):

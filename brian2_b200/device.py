@@ -229,6 +229,8 @@ class B200Device(CPPStandaloneDevice):
 
                 src = owner.source
                 template_kwds["b200_source_size"] = int(len(src)) if isinstance(src, NeuronGroup) else None
+        # seen by the CUDA generator while it translates this code object (pathway direction)
+        self._b200_current_template_kwds = template_kwds
         codeobj = super().code_object(
             owner,
             name,

@@ -34,6 +34,7 @@
                 for (int _k = _beg; _k < _end; ++_k)
                 {
                     const int _idx = _pw.identity ? _k : _pw.syn_ids[_k];
+                    const int _b200_src_idx = _src + _pw.src_start, _b200_tgt_idx = _pw.csr_target[_k];
                     const int _vectorisation_idx = _idx;
                     {% if b200_uses_rng %}
                     b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
@@ -65,20 +66,56 @@
             _spk = b200::compact_slot(_es, _b200_timestep - _delay);
             _nspk = _spk[_es.N];
         }
-        for (int _s = _gwarp; _s < _nspk; _s += _nwarps)
+        if (_nspk <= 0) continue;
+        // Work items = (spike, chunk of its CSR row).  Rows are cut into `_cpr` chunks of `_clen`
+        // slots (a multiple of 32, on 32-slot boundaries: a warp load is one aligned 128-byte line)
+        // so that every warp of the grid has ~2 items even when few neurons with long rows fired;
+        // the warps of a CTA take neighbouring chunks of the same row.
+        const int _maxlen = _pw.bin_maxlen[_bin];
+        int _cpr = (2 * _nwarps + _nspk - 1) / _nspk;
+        if (_cpr > ((_maxlen + 62) >> 5)) _cpr = (_maxlen + 62) >> 5;
+        if (_cpr > 0x7fffffff / _nspk) _cpr = 0x7fffffff / _nspk;
+        if (_cpr < 1) _cpr = 1;
+        const int _clen = (((_maxlen + 31 + _cpr - 1) / _cpr) + 31) & ~31;
+        _cpr = (_maxlen + 31 + _clen - 1) / _clen;
+        if (_cpr < 1) _cpr = 1;
+        const int _nitems = _nspk * _cpr;
+        for (int _it = _gwarp; _it < _nitems; _it += _nwarps)
         {
+            const int _s = _it / _cpr, _ch = _it - _s * _cpr;
             const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
             if (_src < 0 || _src >= _pw.nsrc) continue;
-            const int _beg = _rp[_src], _end = _rp[_src + 1];
-            _nev += (unsigned long long)(_end - _beg);
-            for (int _k = _beg + _lane; _k < _end; _k += 32)
+            const int _rbeg = _rp[_src], _rend = _rp[_src + 1];
+            if (_ch == 0) _nev += (unsigned long long)(_rend - _rbeg);
+            const int _abeg = (_rbeg & ~31) + _ch * _clen;
+            const int _end = min(_rend, _abeg + _clen);
+            const int _b200_src_idx = _src + _pw.src_start;
+            int _k0 = _abeg + _lane;
+            if (_k0 < _rbeg) _k0 += 32;     // first line of the row: lanes in front of its start
+            // {{b200_unroll}} lines of 32 slots per iteration: the loads of the packed index stream(s)
+            // are all in flight before the first reduction is issued
+            for (int _kb = _k0; _kb < _end; _kb += 32 * {{b200_unroll}})
             {
-                const int _idx = _pw.identity ? _k : _pw.syn_ids[_k];
-                const int _vectorisation_idx = _idx;
-                {% if b200_uses_rng %}
-                b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
-                {% endif %}
-                {{vector_code|autoindent}}
+                int _b200_tg[{{b200_unroll}}], _b200_sy[{{b200_unroll}}];
+                #pragma unroll
+                for (int _u = 0; _u < {{b200_unroll}}; ++_u)
+                {
+                    const int _k = _kb + 32 * _u;
+                    _b200_tg[_u] = _k < _end ? __ldg(_pw.csr_target + _k) : 0;
+                    _b200_sy[_u] = (_k < _end && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
+                }
+                #pragma unroll
+                for (int _u = 0; _u < {{b200_unroll}}; ++_u)
+                {
+                    if (_kb + 32 * _u >= _end) break;
+                    const int _idx = _b200_sy[_u];
+                    const int _b200_tgt_idx = _b200_tg[_u];
+                    const int _vectorisation_idx = _idx;
+                    {% if b200_uses_rng %}
+                    b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
+                    {% endif %}
+                    {{vector_code|autoindent}}
+                }
             }
         }
     }
