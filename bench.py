@@ -46,6 +46,12 @@ WORKLOADS = {
 }
 
 
+# simulation timesteps (dt = 0.1 ms) of one bench step = one run() call
+DEFAULT_SIM_STEPS = {"cobahh_256k": 4000, "cuba_256k": 4000, "cuba_4k": 10000, "cobahh_4k": 10000,
+                     "brunel_100k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
+                     "synapses_only_highrate": 500}
+
+
 def _n_neurons(objs):
     for key in ("P", "neurons", "H"):
         if key in objs:
@@ -62,53 +68,67 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples (NVML, every ~2 ms) kept only when they fall inside
+    the timed step loops (`windows` = [(t0, t1)] in host epoch seconds)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.samples = []
-        self.proc = None
         self.index = index
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        self.error = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:  # no NVML: report it, never fake a clock
+            self.error = f"nvml unavailable: {ex}"
             return
-        threading.Thread(target=self._reader, daemon=True).start()
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
 
-    def _reader(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [s for (ts, s) in self.samples if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.2)]
-        if not rows:
-            rows = [s for (_, s) in self.samples]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            parts = [p.strip() for p in r.split(",")]
+    def _poll(self):
+        nv, h = self._nvml, self._h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, parts[2:]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = reasons_fn(h)
+                self.samples.append((time.time(), float(mhz), int(mask)))
+            except Exception as ex:
+                self.error = str(ex)
+                return
+            time.sleep(0.002)
+
+    def stop(self, windows=None):
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "no samples"]}
+        self._stop.set()
+        self._thread.join()
+        rows = [(mhz, mask) for (ts, mhz, mask) in self.samples
+                if not windows or any(t0 <= ts <= t1 for (t0, t1) in windows)]
+        where = "inside the timed step loops"
+        if not rows:
+            rows = [(mhz, mask) for (_, mhz, mask) in self.samples]
+            where = "whole run (no sample fell inside a timed loop)"
+        sm = sorted(m for m, _ in rows)
+        reasons = set()
+        for _, mask in rows:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": where}
 
 
 def _import_brian():
@@ -184,7 +204,7 @@ def run_b200(args, rank, world):
     b = _import_brian()
     if world > 1:
         _barrier(world)   # initialises the process group: the device shards over its ranks
-    sim_steps = args.sim_steps or 500
+    sim_steps = args.sim_steps or DEFAULT_SIM_STEPS.get(args.workload, 2000)
     n_runs = args.warmup + args.steps
     directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
     t_build0 = time.time()
@@ -206,11 +226,12 @@ def run_b200(args, rank, world):
     t0 = time.time()
     b.device.run(directory=directory, with_output=False)
     t1 = time.time()
-    clocks = sampler.stop(t0, t1)
     cnt = b.device.counter
     runs = int(cnt("runs"))
     assert runs == n_runs, (runs, n_runs)
     timed = range(args.warmup, n_runs)
+    clocks = sampler.stop([(cnt(f"run{r}.t0_unix"), cnt(f"run{r}.t0_unix") + cnt(f"run{r}.wall_seconds"))
+                           for r in timed])
     dev_s = sum(cnt(f"run{r}.device_seconds") for r in timed)
     e2e_s = sum(cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds") + cnt(f"run{r}.download_seconds")
                 for r in timed)

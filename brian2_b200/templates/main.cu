@@ -179,6 +179,7 @@ double b200_get_counter(const char* key)
                 const B200RunRecord& r = Network::_b200_run_log[i];
                 if (f == "device_seconds") return r.device_seconds;
                 if (f == "wall_seconds") return r.wall_seconds;
+                if (f == "t0_unix") return r.t0_unix;
                 if (f == "upload_seconds") return r.upload_seconds;
                 if (f == "download_seconds") return r.download_seconds;
                 if (f == "events") return r.events;

@@ -85,6 +85,7 @@ void Network::run(const double duration, void (*report_func)(const double, const
     B200_CUDA(cudaDeviceSynchronize());
     B200_CUDA(cudaEventRecord(_ev_start, b200::state().stream));
     hrc::time_point start = hrc::now(), current;
+    const double _t0_unix = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
     if (report_func)
         report_func(0.0, 0.0, t_start, duration);
 
@@ -204,6 +205,7 @@ void Network::run(const double duration, void (*report_func)(const double, const
         B200_CUDA(cudaEventElapsedTime(&ms, _ev_start, _ev_stop));
         rec.device_seconds = 1e-3 * ms;
         rec.wall_seconds = elapsed_realtime;
+        rec.t0_unix = _t0_unix;
         rec.steps = Network::_b200_steps_run - _steps_before;
         rec.events = (double)(_b200_events_delivered() - _events_before);
         rec.upload_seconds = b200::state().upload_seconds - _upload_before;
@@ -237,6 +239,7 @@ struct B200Plan {
 struct B200RunRecord {
     double device_seconds;     // CUDA-event time of the step loop
     double wall_seconds;       // host clock around the same region
+    double t0_unix;            // host time (seconds since the epoch) when the loop started
     double upload_seconds, download_seconds;
     double events;             // synaptic events delivered during this run
     long long steps;

@@ -49,40 +49,66 @@
     const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
     const int _nwarps = _ctx.nb * b200::kWarps;
     unsigned long long _nev = 0ULL;
-    for (int _bin = 0; _bin < _pw.nbins; ++_bin)
+    // The list of the current step (delay 0) is read from the thresholder's segments
+    b200::SpikeView _view;
+    _view.total = 0;
+    if (_pw.nbins > 0 && _pw.bin_delay[0] == 0)
+        _view = b200::view_build(_es, _b200_timestep, _ctx, false, _A._ctrl);
+    // Work items = (delay bin, spike of that bin's step, chunk of its CSR row), flattened over all
+    // bins so that one pass of the grid covers them (the bins are independent: no latency chain
+    // per bin).  Lane l of every warp holds the parameters of bin _g0 + l; an item finds its bin
+    // with one ballot.  Rows are cut into `_cpr` chunks of `_clen` slots (a multiple of 32, on
+    // 32-slot boundaries: a warp load is one aligned 128-byte line) so that every warp of the
+    // grid has ~2 items even when few neurons with long rows fired; the warps of a CTA take
+    // neighbouring chunks of the same row.
+    for (int _g0 = 0; _g0 < _pw.nbins; _g0 += 32)
     {
-        const int _delay = _pw.bin_delay[_bin];
-        const int* _rp = _pw.rowptr + (size_t)_bin * (_pw.nsrc + 1);
-        b200::SpikeView _view;
-        const int32_t* _spk = 0;
-        int _nspk;
-        if (_delay == 0)
+        const int _mybin = _g0 + _lane;
+        int _bdelay = 0, _bn = 0, _bmax = 0;
+        const int32_t* _bspk = 0;
+        if (_mybin < _pw.nbins)
         {
-            _view = b200::view_build(_es, _b200_timestep, _ctx, false, _A._ctrl);
-            _nspk = _view.total;
+            _bdelay = _pw.bin_delay[_mybin];
+            _bmax = _pw.bin_maxlen[_mybin];
+            if (_bdelay == 0)
+                _bn = _view.total;
+            else
+            {
+                _bspk = b200::compact_slot(_es, _b200_timestep - _bdelay);
+                _bn = _bspk[_es.N];
+            }
         }
-        else
+        int _rows = _bn;
+        #pragma unroll
+        for (int _o = 16; _o > 0; _o >>= 1) _rows += __shfl_xor_sync(0xffffffffu, _rows, _o);
+        if (_rows <= 0) continue;
+        int _bcpr = (2 * _nwarps + _rows - 1) / _rows;
+        if (_bcpr > ((_bmax + 62) >> 5)) _bcpr = (_bmax + 62) >> 5;
+        if (_bcpr > 0x7fffffff / _rows) _bcpr = 0x7fffffff / _rows;
+        if (_bcpr < 1) _bcpr = 1;
+        const int _bclen = (((_bmax + 31 + _bcpr - 1) / _bcpr) + 31) & ~31;
+        _bcpr = (_bmax + 31 + _bclen - 1) / _bclen;
+        if (_bcpr < 1) _bcpr = 1;
+        const int _bitems = _bn * _bcpr;
+        int _bincl = _bitems;
+        #pragma unroll
+        for (int _o = 1; _o < 32; _o <<= 1)
         {
-            _spk = b200::compact_slot(_es, _b200_timestep - _delay);
-            _nspk = _spk[_es.N];
+            const int _t = __shfl_up_sync(0xffffffffu, _bincl, _o);
+            if (_lane >= _o) _bincl += _t;
         }
-        if (_nspk <= 0) continue;
-        // Work items = (spike, chunk of its CSR row).  Rows are cut into `_cpr` chunks of `_clen`
-        // slots (a multiple of 32, on 32-slot boundaries: a warp load is one aligned 128-byte line)
-        // so that every warp of the grid has ~2 items even when few neurons with long rows fired;
-        // the warps of a CTA take neighbouring chunks of the same row.
-        const int _maxlen = _pw.bin_maxlen[_bin];
-        int _cpr = (2 * _nwarps + _nspk - 1) / _nspk;
-        if (_cpr > ((_maxlen + 62) >> 5)) _cpr = (_maxlen + 62) >> 5;
-        if (_cpr > 0x7fffffff / _nspk) _cpr = 0x7fffffff / _nspk;
-        if (_cpr < 1) _cpr = 1;
-        const int _clen = (((_maxlen + 31 + _cpr - 1) / _cpr) + 31) & ~31;
-        _cpr = (_maxlen + 31 + _clen - 1) / _clen;
-        if (_cpr < 1) _cpr = 1;
-        const int _nitems = _nspk * _cpr;
+        const int _bexcl = _bincl - _bitems;
+        const int _nitems = __shfl_sync(0xffffffffu, _bincl, 31);
         for (int _it = _gwarp; _it < _nitems; _it += _nwarps)
         {
-            const int _s = _it / _cpr, _ch = _it - _s * _cpr;
+            const int _L = 31 - __clz(__ballot_sync(0xffffffffu, _bexcl <= _it));
+            const int _loc = _it - __shfl_sync(0xffffffffu, _bexcl, _L);
+            const int _cpr = __shfl_sync(0xffffffffu, _bcpr, _L);
+            const int _clen = __shfl_sync(0xffffffffu, _bclen, _L);
+            const int _delay = __shfl_sync(0xffffffffu, _bdelay, _L);
+            const int32_t* _spk = (const int32_t*)__shfl_sync(0xffffffffu, (unsigned long long)_bspk, _L);
+            const int* _rp = _pw.rowptr + (size_t)(_g0 + _L) * (_pw.nsrc + 1);
+            const int _s = _loc / _cpr, _ch = _loc - _s * _cpr;
             const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
             if (_src < 0 || _src >= _pw.nsrc) continue;
             const int _rbeg = _rp[_src], _rend = _rp[_src + 1];
