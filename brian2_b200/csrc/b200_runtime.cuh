@@ -85,10 +85,20 @@ __host__ __device__ __forceinline__ unsigned long long id_tag(int64_t timestep) 
 // Grid barrier for the persistent kernel.  Monotonic 64-bit arrival counter (never reset inside
 // a launch); `target` is thread-0 private state.  Release on arrival, acquire fence after the wait
 // (the gpu-scope fence also invalidates this SM's L1, so plain loads after the barrier see other
-// CTAs' writes).
+// CTAs' writes).  Bit 62 of the counter word is the "leave the step loop" flag: whoever raises
+// it does so before its own arrival, so the value a poller finally sees carries the flag and the
+// end-of-step check costs no extra round trip to L2.  Returns the flag (to all threads).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target,
+constexpr unsigned long long kStopBit = 1ULL << 62;
+
+__device__ __forceinline__ void raise_stop(Control* ctrl) {
+    ctrl->stop = 1;
+    atomicOr(&ctrl->barrier, kStopBit);
+}
+
+__device__ __forceinline__ bool grid_barrier(unsigned long long* counter, unsigned long long& target,
                                              const Ctx& c) {
+    __shared__ int s_flag;
     __syncthreads();
     if (threadIdx.x == 0) {
         target += (unsigned long long)c.gnb;
@@ -97,11 +107,14 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
         asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ULL) : "memory");
         // wait: relaxed polls (served by L2, no L1 invalidation per iteration), one acquire
         // fence at the end -- it also drops this SM's stale L1 lines for the plain loads that follow
-        while (ld_relaxed_u64(counter) < target) {
+        unsigned long long v;
+        while (((v = ld_relaxed_u64(counter)) & ~kStopBit) < target) {
         }
+        s_flag = (v & kStopBit) ? 1 : 0;
         __threadfence();
     }
     __syncthreads();
+    return s_flag != 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -134,23 +147,63 @@ __host__ __device__ __forceinline__ int64_t warp_first(int64_t lo, int64_t hi, i
     return e < hi ? e : hi;
 }
 
+// The slices of a launch never change, and the division above is ~100 instructions: a small
+// per-CTA cache in shared memory keeps the first element of every warp of the CTA for the last
+// few group sizes seen.  COLLECTIVE: every thread of the CTA must call owned_slice/owned_cta at
+// the same point with the same N (true for all per-element templates); a miss synchronises.
+constexpr int kSliceCache = 4;
+struct SliceCache {
+    long long N[kSliceCache];
+    long long first[kSliceCache][kWarps + 1];
+    int next;
+};
+__device__ __forceinline__ SliceCache& slice_cache() {
+    __shared__ SliceCache sc;
+    return sc;
+}
+// to be called once at kernel start (before the first __syncthreads)
+__device__ __forceinline__ void slice_cache_reset() {
+    SliceCache& sc = slice_cache();
+    if (threadIdx.x < kSliceCache) sc.N[threadIdx.x] = -1;
+    if (threadIdx.x == 0) sc.next = 0;
+}
+__device__ __forceinline__ int slice_cache_slot(int64_t N, const Ctx& c) {
+    SliceCache& sc = slice_cache();
+    int slot = -1;
+#pragma unroll
+    for (int k = 0; k < kSliceCache; ++k)
+        if (sc.N[k] == (long long)N) slot = k;
+    if (slot < 0) {             // uniform over the CTA
+        __syncthreads();
+        slot = sc.next;
+        if (threadIdx.x <= kWarps) {
+            int64_t lo, hi;
+            rank_range(N, c.rank, c.world, lo, hi);
+            sc.first[slot][threadIdx.x] = warp_first(lo, hi, (int64_t)c.gbid * kWarps + threadIdx.x,
+                                                     (int64_t)c.gnb * kWarps);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { sc.N[slot] = (long long)N; sc.next = (slot + 1) % kSliceCache; }
+        __syncthreads();
+    }
+    return slot;
+}
+
 __device__ __forceinline__ Slice owned_slice(int64_t N, const Ctx& c) {
-    int64_t lo, hi;
-    rank_range(N, c.rank, c.world, lo, hi);
-    const int64_t g = (int64_t)c.gbid * kWarps + (threadIdx.x >> 5), G = (int64_t)c.gnb * kWarps;
+    const int slot = slice_cache_slot(N, c);
+    const SliceCache& sc = slice_cache();
     Slice s;
-    s.lo = warp_first(lo, hi, g, G);
-    s.hi = warp_first(lo, hi, g + 1, G);
+    s.lo = sc.first[slot][threadIdx.x >> 5];
+    s.hi = sc.first[slot][(threadIdx.x >> 5) + 1];
     return s;
 }
 // the elements owned by the whole CTA
 __device__ __forceinline__ Slice owned_cta(int64_t N, const Ctx& c) {
-    int64_t lo, hi;
-    rank_range(N, c.rank, c.world, lo, hi);
-    const int64_t G = (int64_t)c.gnb * kWarps;
+    const int slot = slice_cache_slot(N, c);
+    const SliceCache& sc = slice_cache();
     Slice s;
-    s.lo = warp_first(lo, hi, (int64_t)c.gbid * kWarps, G);
-    s.hi = warp_first(lo, hi, (int64_t)(c.gbid + 1) * kWarps, G);
+    s.lo = sc.first[slot][0];
+    s.hi = sc.first[slot][kWarps];
     return s;
 }
 
@@ -257,6 +310,7 @@ __device__ __forceinline__ void view_reset() {
     long long* tag;
     view_storage(&tag);
     if (threadIdx.x == 0) *tag = 0;
+    slice_cache_reset();
     __syncthreads();
 }
 
@@ -300,6 +354,7 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
                     while (((w = ld_volatile_s32(wp)) >> 16) != want) {
                         if (clock64() - t0 > 40000000000LL || ld_volatile_s32(&ctrl->error)) {   // ~20 s
                             ctrl->error = 1;
+                            raise_stop(ctrl);
                             w = 0;
                             break;
                         }

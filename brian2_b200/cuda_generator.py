@@ -228,6 +228,13 @@ class CUDANodeRenderer(CPPNodeRenderer):
         super().__init__(auto_vectorise=auto_vectorise)
         self.fuse_exp_pow = fuse_exp_pow
 
+    # exp/expm1 -> constant-bank versions of the same algorithms (csrc/b200_functions.cuh);
+    # on the host (hoisted loop-invariant scalars) they are the libm functions
+    _DEVICE_MATH = {"exp": "_b200_exp", "expm1": "_b200_expm1"}
+
+    def render_func(self, node):
+        return self._DEVICE_MATH.get(node.id, super().render_func(node))
+
     def render_BinOp(self, node):
         if (
             self.fuse_exp_pow

@@ -129,7 +129,6 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
 {
     const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     unsigned long long _bar_target = 0ULL;
-    __shared__ int _s_stop;
     _B200Clocks _clks = _clks0;
     long long _step = 0;
     b200::view_reset();
@@ -144,7 +143,7 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         // the stop flag lives in host memory (one PCIe round trip per poll): look at it every
         // 64 steps only -- a stop request is honoured within a few milliseconds
         if ((_step & 63) == 0 && _ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
-            _A._ctrl->stop = 1;
+            b200::raise_stop(_A._ctrl);
         {% for item in plan.entries %}
         {% if item.barrier %}
         b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
@@ -175,17 +174,13 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         {% endif %}
         B200_PHASE({{2 * loop.index0 + 1}})
         {% endfor %}
-        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        const bool _stop = b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
         B200_PHASE({{2 * (plan.entries | length)}})
-        if (threadIdx.x == 0) _s_stop = b200::ld_volatile_s32(&_A._ctrl->stop) | b200::ld_volatile_s32(&_A._ctrl->error);
-        __syncthreads();
-        const int _stop = _s_stop;
         // Clock::tick (brianlib/clocks.h:34-38)
         _clks.{{plan.clock}}.timestep += 1;
         _clks.{{plan.clock}}.t = _clks.{{plan.clock}}.timestep * _clks.{{plan.clock}}.dt;
         ++_step;
         if (_stop) break;
-        __syncthreads();
     }
     if (_ctx.bid == 0 && threadIdx.x == 0) _A._ctrl->steps_done = (int)_step;
 }

@@ -50,7 +50,7 @@
         if (_N_new + (long long)(_source_stop - _source_start) > (long long)_A._cap{{b200_field(_first)}})
         {
             _A._ctrl->overflow = 1;
-            _A._ctrl->stop = 1;
+            b200::raise_stop(_A._ctrl);
         }
         {% endif %}
     }

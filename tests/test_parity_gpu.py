@@ -81,6 +81,26 @@ def test_in_loop_random_numbers_statistics(brian, project_dir):
     np.testing.assert_allclose(res["G_v"].mean(), gold["G_v"].mean(), rtol=0.1)
 
 
+def test_device_math_identical(tmp_path):
+    """The constant-bank exp/expm1/exprel of csrc/b200_functions.cuh return the same bits as CUDA's
+    library functions (with which the parity tolerances above were established) for 4 x 2^24
+    arguments: arbitrary bit patterns, the Hodgkin-Huxley range, the overflow range, tiny values."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    here = os.path.dirname(__file__)
+    exe = str(tmp_path / "math_identical")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false",
+                           "-I", os.path.join(here, "..", "brian2_b200", "csrc"), "-o", exe,
+                           os.path.join(here, "cuda", "math_identical.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    rows = dict((ln.split()[0], ln.split()[1:]) for ln in out.stdout.strip().splitlines())
+    for fn in ("exp", "expm1", "exprel"):
+        assert fn in rows, out.stdout + out.stderr
+        assert int(rows[fn][0]) == 4 << 24 and int(rows[fn][1]) == 0, (fn, rows[fn])
+
+
 def _gpu_count():
     try:
         import torch
