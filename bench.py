@@ -244,8 +244,9 @@ def run_b200(args, rank, world):
                          f"acquire fence {cnt('fence_cycles') / n / 1.965e3:.3f} us per wait\n")
     if args.phases:
         total_steps = cnt("steps")
-        for name, cyc in b.device.phase_profile():
-            sys.stderr.write(f"PHASE r{rank} {name:55s} {cyc / total_steps / 1.965e3:8.3f} us/step\n")
+        for name, cycs in b.device.phase_profile(all_ctas=True):
+            cols = " ".join(f"{c / total_steps / 1.965e3:8.3f}" for c in cycs)
+            sys.stderr.write(f"PHASE r{rank} {name:55s} {cols}  us/step (CTA 0, 1/4, 3/4, last)\n")
     model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
     n_neurons = _n_neurons(objs)
     n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))

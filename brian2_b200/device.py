@@ -1076,7 +1076,7 @@ class B200Device(CPPStandaloneDevice):
         if comm.world > 1:
             self._merge_multi_gpu_results(comm)
 
-    def phase_profile(self, plan=0):
+    def phase_profile(self, plan=0, all_ctas=False):
         """[(phase name, SM cycles spent by CTA 0)] of the persistent kernel of run() call `plan`
         (needs ``prefs.devices.b200.profile_phases = True`` at build time)."""
         info = self._b200_plan_info[plan]
@@ -1086,7 +1086,11 @@ class B200Device(CPPStandaloneDevice):
         for it in info["entries"]:
             names += ["barrier" if it["barrier"] else None, it["name"]]
         names.append("end-of-step barrier")
-        return [(n, self.counter(f"phase{i}")) for i, n in enumerate(names) if n is not None]
+        if not all_ctas:
+            return [(n, self.counter(f"phase{i}")) for i, n in enumerate(names) if n is not None]
+        # cycles of the four sampled CTAs (first, 1/4, 3/4, last of the grid)
+        return [(n, [self.counter(f"phase{k * 512 + i}") for k in range(4)])
+                for i, n in enumerate(names) if n is not None]
 
     # counters of the last run (for benchmarks)
     def counter(self, key):

@@ -134,7 +134,9 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     b200::view_reset();
     {% if profile_phases %}
     long long _pt = clock64();
-    #define B200_PHASE(i) if (_ctx.bid == 0 && threadIdx.x == 0) { const long long _now = clock64(); _A._prof[i] += (unsigned long long)(_now - _pt); _pt = _now; }
+    // four sampled CTAs (first, 1/4, 3/4, last of the grid): slot k * 512 + phase
+    const int _pk = _ctx.gbid == 0 ? 0 : (_ctx.gbid == _ctx.gnb / 4 ? 1 : (_ctx.gbid == (3 * _ctx.gnb) / 4 ? 2 : (_ctx.gbid == _ctx.gnb - 1 ? 3 : -1)));
+    #define B200_PHASE(i) if (_pk >= 0 && threadIdx.x == 0) { const long long _now = clock64(); _A._prof[_pk * 512 + (i)] += (unsigned long long)(_now - _pt); _pt = _now; }
     {% else %}
     #define B200_PHASE(i)
     {% endif %}

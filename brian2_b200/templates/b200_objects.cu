@@ -161,8 +161,8 @@ void _b200_upload()
     // event spaces (history survives between runs); on several GPUs the rings are mapped into
     // every peer once per allocation (CUDA IPC handles travel through the allgather callback)
     if (!_A_host._prof) {
-        _A_host._prof = (unsigned long long*)b200::dev_alloc(512 * sizeof(unsigned long long));
-        B200_CUDA(cudaMemset(_A_host._prof, 0, 512 * sizeof(unsigned long long)));
+        _A_host._prof = (unsigned long long*)b200::dev_alloc(4 * 512 * sizeof(unsigned long long));
+        B200_CUDA(cudaMemset(_A_host._prof, 0, 4 * 512 * sizeof(unsigned long long)));
     }
     _A_host._rank = st.rank;
     _A_host._world = st.world;

@@ -165,7 +165,7 @@ double b200_get_counter(const char* key)
     if (k.compare(0, 5, "phase") == 0) {   // "phase<i>": cycles CTA 0 spent in phase i (profile_phases)
         const int i = atoi(k.c_str() + 5);
         unsigned long long v = 0;
-        if (i < 0 || i >= 512 || !_A_host._prof) return -1.0;
+        if (i < 0 || i >= 4 * 512 || !_A_host._prof) return -1.0;
         cudaMemcpy(&v, _A_host._prof + i, sizeof(v), cudaMemcpyDeviceToHost);
         return (double)v;
     }

@@ -12,6 +12,10 @@
 {% extends 'common_group.cu' %}
 {% block maincode %}
     const b200::EventSpaceDev& _es = _A._es{{get_array_name(eventspace_variable, access_data=False)}};
+    // (issued first: this load is in flight while the view is built)
+    const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
+    long long* _monN = _A._monN_{{owner.name}};
+    const long long _N_old = b200::ld_relaxed_s64(_monN + _par);
     const b200::SpikeView _view = b200::view_build(_es, _clks.{{b200_clock}}.timestep, _ctx, true, _A._ctrl);
     int _start_idx = 0, _end_idx = _view.total;
     if ((int)_source_start > 0 || (int)_source_stop < _es.N)
@@ -20,9 +24,6 @@
         _end_idx = b200::view_count_below(_view, _es, (int)_source_stop);
     }
     const int _num_events = _end_idx - _start_idx;
-    const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
-    long long* _monN = _A._monN_{{owner.name}};
-    const long long _N_old = _monN[_par];
     if (_num_events > 0)
     {
         const int _vectorisation_idx = 1;
@@ -37,7 +38,8 @@
             {% for varname, var in record_variables | dictsort %}
             _A.{{b200_field(var)}}[_out] = _to_record_{{varname}};
             {% endfor %}
-            {{count}}[_idx - _source_start]++;
+            // (the ids of one step are distinct: a reduction without return value, no round trip)
+            atomicAdd(&{{count}}[_idx - _source_start], 1);
         }
     }
     if (_ctx.bid == 0 && threadIdx.x == 0)

@@ -54,22 +54,24 @@
     _view.total = 0;
     if (_pw.nbins > 0 && _pw.bin_delay[0] == 0)
         _view = b200::view_build(_es, _b200_timestep, _ctx, false, _A._ctrl);
-    // Work items = (delay bin, spike of that bin's step, chunk of its CSR row), flattened over all
-    // bins so that one pass of the grid covers them (the bins are independent: no latency chain
-    // per bin).  Lane l of every warp holds the parameters of bin _g0 + l; an item finds its bin
-    // with one ballot.  Rows are cut into `_cpr` chunks of `_clen` slots (a multiple of 32, on
-    // 32-slot boundaries: a warp load is one aligned 128-byte line) so that every warp of the
-    // grid has ~2 items even when few neurons with long rows fired; the warps of a CTA take
-    // neighbouring chunks of the same row.
+    // Work = 128-byte lines of the packed index stream.  Every (delay bin, spike of that bin's
+    // step) row is padded to the bin's longest row (`_lr` lines of 32 slots, on 32-slot boundaries:
+    // a warp load is one aligned line) and the lines of all rows of all bins form one virtual
+    // sequence that is dealt out to the warps of the grid in equal contiguous shares: balanced
+    // to within one line whether few neurons with long rows or many with short rows fired, and
+    // neighbouring warps read neighbouring lines of the same row.  Lane l of every warp holds the
+    // parameters of bin _g0 + l; a line finds its bin with one ballot (the bins are independent:
+    // no latency chain per bin).
     for (int _g0 = 0; _g0 < _pw.nbins; _g0 += 32)
     {
         const int _mybin = _g0 + _lane;
-        int _bdelay = 0, _bn = 0, _bmax = 0;
+        int _bdelay = 0, _bn = 0, _blr = 1;
         const int32_t* _bspk = 0;
         if (_mybin < _pw.nbins)
         {
             _bdelay = _pw.bin_delay[_mybin];
-            _bmax = _pw.bin_maxlen[_mybin];
+            _blr = (_pw.bin_maxlen[_mybin] + 62) >> 5;
+            if (_blr < 1) _blr = 1;
             if (_bdelay == 0)
                 _bn = _view.total;
             else
@@ -78,43 +80,42 @@
                 _bn = _bspk[_es.N];
             }
         }
-        int _rows = _bn;
-        #pragma unroll
-        for (int _o = 16; _o > 0; _o >>= 1) _rows += __shfl_xor_sync(0xffffffffu, _rows, _o);
-        if (_rows <= 0) continue;
-        int _bcpr = (2 * _nwarps + _rows - 1) / _rows;
-        if (_bcpr > ((_bmax + 62) >> 5)) _bcpr = (_bmax + 62) >> 5;
-        if (_bcpr > 0x7fffffff / _rows) _bcpr = 0x7fffffff / _rows;
-        if (_bcpr < 1) _bcpr = 1;
-        const int _bclen = (((_bmax + 31 + _bcpr - 1) / _bcpr) + 31) & ~31;
-        _bcpr = (_bmax + 31 + _bclen - 1) / _bclen;
-        if (_bcpr < 1) _bcpr = 1;
-        const int _bitems = _bn * _bcpr;
-        int _bincl = _bitems;
+        long long _blines = (long long)_bn * _blr;
+        long long _bincl = _blines;
         #pragma unroll
         for (int _o = 1; _o < 32; _o <<= 1)
         {
-            const int _t = __shfl_up_sync(0xffffffffu, _bincl, _o);
+            const long long _t = __shfl_up_sync(0xffffffffu, _bincl, _o);
             if (_lane >= _o) _bincl += _t;
         }
-        const int _bexcl = _bincl - _bitems;
-        const int _nitems = __shfl_sync(0xffffffffu, _bincl, 31);
-        for (int _it = _gwarp; _it < _nitems; _it += _nwarps)
+        const long long _bexcl = _bincl - _blines;
+        const long long _nlines = __shfl_sync(0xffffffffu, _bincl, 31);
+        if (_nlines <= 0) continue;
+        // (32-bit divisions whenever the numbers allow: ~10x cheaper)
+        const bool _small = _nlines * (long long)_nwarps < 0xffffffffLL;
+        long long _a = _small ? (long long)(((unsigned int)_gwarp * (unsigned int)_nlines) / (unsigned int)_nwarps)
+                              : ((long long)_gwarp * _nlines) / _nwarps;
+        const long long _b = _small ? (long long)(((unsigned int)(_gwarp + 1) * (unsigned int)_nlines) / (unsigned int)_nwarps)
+                                    : ((long long)(_gwarp + 1) * _nlines) / _nwarps;
+        while (_a < _b)
         {
-            const int _L = 31 - __clz(__ballot_sync(0xffffffffu, _bexcl <= _it));
-            const int _loc = _it - __shfl_sync(0xffffffffu, _bexcl, _L);
-            const int _cpr = __shfl_sync(0xffffffffu, _bcpr, _L);
-            const int _clen = __shfl_sync(0xffffffffu, _bclen, _L);
+            const int _L = 31 - __clz(__ballot_sync(0xffffffffu, _bexcl <= _a));
+            const long long _loc = _a - __shfl_sync(0xffffffffu, _bexcl, _L);
+            const int _lr = __shfl_sync(0xffffffffu, _blr, _L);
             const int _delay = __shfl_sync(0xffffffffu, _bdelay, _L);
             const int32_t* _spk = (const int32_t*)__shfl_sync(0xffffffffu, (unsigned long long)_bspk, _L);
             const int* _rp = _pw.rowptr + (size_t)(_g0 + _L) * (_pw.nsrc + 1);
-            const int _s = _loc / _cpr, _ch = _loc - _s * _cpr;
+            const int _s = _small ? (int)((unsigned int)_loc / (unsigned int)_lr) : (int)(_loc / _lr);
+            const int _l0 = (int)(_loc - (long long)_s * _lr);
+            // lines of this row inside my share
+            const int _nl = (int)min((long long)(_lr - _l0), _b - _a);
+            _a += _nl;
             const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
             if (_src < 0 || _src >= _pw.nsrc) continue;
             const int _rbeg = _rp[_src], _rend = _rp[_src + 1];
-            if (_ch == 0) _nev += (unsigned long long)(_rend - _rbeg);
-            const int _abeg = (_rbeg & ~31) + _ch * _clen;
-            const int _end = min(_rend, _abeg + _clen);
+            if (_l0 == 0) _nev += (unsigned long long)(_rend - _rbeg);
+            const int _abeg = (_rbeg & ~31) + 32 * _l0;
+            const int _end = min(_rend, _abeg + 32 * _nl);
             const int _b200_src_idx = _src + _pw.src_start;
             int _k0 = _abeg + _lane;
             if (_k0 < _rbeg) _k0 += 32;     // first line of the row: lanes in front of its start
