@@ -176,6 +176,7 @@ struct EventSpace {
     void* peer_ids[kMaxRanks] = {0};
     void* peer_cnt[kMaxRanks] = {0};
     bool peers_open = false;
+    bool compact_always = false;   // a consumer walks the compact list of the current step
 
     void require(int dmin, int dmax) {
         max_delay = std::max(max_delay, dmax);
@@ -279,6 +280,8 @@ struct EventSpace {
         memset(&v, 0, sizeof(v));
         v.ids = ids; v.cnt = cnt; v.compact = compact; v.seg_start = seg_start;
         v.slots = slots; v.N = N; v.nseg = nseg; v.lag = lag(); v.id = id;
+        // the reference layout is only built when somebody reads it (delayed or serial pathways)
+        v.need_compact = (compact_always || max_delay > 0) ? 1 : 0;
         int64_t lo, hi;
         rank_range_host(N, st.rank, st.world, lo, hi);
         v.rank_lo = (int)lo; v.rank_hi = (int)hi;
@@ -315,6 +318,7 @@ public:
     int* d_syn_ids = nullptr;
     int* d_csr_target = nullptr;
     unsigned long long* d_events = nullptr;
+    unsigned int* d_tickets = nullptr;
     EventSpace* es = nullptr;
     size_t n_owned = 0;            // synapses stored on this rank (post neuron owned)
 
@@ -437,6 +441,8 @@ public:
             d_events = (unsigned long long*)dev_alloc(sizeof(unsigned long long));
             B200_CUDA(cudaMemset(d_events, 0, sizeof(unsigned long long)));
         }
+        if (!d_tickets) d_tickets = (unsigned int*)dev_alloc(2 * sizeof(unsigned int));
+        B200_CUDA(cudaMemset(d_tickets, 0, 2 * sizeof(unsigned int)));
         if (es) es->require(bin_delay.empty() ? 0 : bin_delay.front(), max_delay);
         prepared = true;
     }
@@ -447,6 +453,7 @@ public:
         v.src_start = spikes_start;
         v.nbins = nbins;
         v.identity = identity ? 1 : 0;
+        v.has_delay0 = (!bin_delay.empty() && bin_delay.front() == 0) ? 1 : 0;
         v.bin_delay = d_bin_delay;
         v.bin_maxlen = d_bin_delay + nbins;
         v.rowptr = d_rowptr;
@@ -454,6 +461,7 @@ public:
         v.csr_target = d_csr_target;
         v.es = es ? es->id : -1;
         v.events = d_events;
+        v.tickets = d_tickets;
         return v;
     }
 

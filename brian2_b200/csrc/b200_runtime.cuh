@@ -451,13 +451,13 @@ __device__ __forceinline__ int view_count_below(const SpikeView& v, const EventS
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void compact_segments(const EventSpaceDev& es, int64_t timestep, const Ctx& c,
                                                  Control* ctrl) {
+    if (!es.need_compact) return;
     const int64_t s = timestep - es.lag;
     const SpikeView v = view_build(es, s, c, false, ctrl);
     int32_t* out = es.compact + (size_t)ring_index(s, es.slots) * (size_t)(es.N + 1);
-    for (int j = c.bid; j < v.nseg; j += c.nb) {
-        const int beg = v.pref[j], cnt = v.pref[j + 1] - beg;
-        for (int k = threadIdx.x; k < cnt; k += kBlock) out[beg + k] = view_load(v, j, k);
-    }
+    // one spike per thread: all loads of the step are in flight together (a CTA walking whole
+    // segments would pay one round trip to L2 per segment)
+    for (int g = c.bid * kBlock + (int)threadIdx.x; g < v.total; g += c.nb * kBlock) out[g] = view_id(v, g);
     if (c.bid == 0 && threadIdx.x == 0) out[es.N] = v.total;
 }
 

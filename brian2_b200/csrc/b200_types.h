@@ -53,6 +53,7 @@ struct EventSpaceDev {
     int nseg;                 // world * nb
     int lag;                  // compaction of step s happens during step s + lag
     int id;                   // index of this event space (tag of the cached view)
+    int need_compact;         // 0: nobody reads the compact form (no delayed / serial pathway)
     int rank_lo, rank_hi;     // neurons owned by this rank
     // multi-GPU: the peers' rings (CUDA IPC mapped)
     unsigned long long* peer_ids[kMaxRanks];
@@ -65,6 +66,7 @@ struct PathwayDev {
     int src_start;            // first source id in the parent group (spikequeue.h:97,162)
     int nbins;                // distinct integer delays
     int identity;             // 1: csr slot k == synapse index k (no indirection needed)
+    int has_delay0;           // 1: the first bin has delay 0 (the current step's list is needed)
     const int* bin_delay;     // [nbins] delay in steps, ascending
     const int* bin_maxlen;    // [nbins] length of the longest row of the bin
     const int* rowptr;        // [nbins*(nsrc+1)+1] slot offsets
@@ -72,6 +74,7 @@ struct PathwayDev {
     const int* csr_target;    // [S] the non-source end of the synapse, packed in slot order
     int es;                   // (unused on the device; kept for debugging)
     unsigned long long* events;   // number of delivered synaptic events (for the metric)
+    unsigned int* tickets;        // [2] work counters of heavy steps (by step parity)
 };
 
 // Device view of a by-target index of a Synapses object (summed variables): row t lists the

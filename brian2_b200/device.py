@@ -481,7 +481,7 @@ class B200Device(CPPStandaloneDevice):
                 continue
             pr, pw, sr, sw = self._codeobj_access(codeobj)
             add(codeobj.name, "codeobj", pr, pw, sr, sw, owned=self._is_owned_type(codeobj),
-                extra={"weight": 6 if info["template"] == "synapses" else 1})
+                extra={"weight": 24 if info["template"] == "synapses" else 1})
             if info["template"] in SPIKE_SOURCE_TEMPLATES:
                 es = info["template_kwds"]["eventspace_variable"]
                 ph_thresholders.append(
@@ -667,7 +667,20 @@ class B200Device(CPPStandaloneDevice):
                         "name": self.arrays[var],
                         "size": int(var.size),
                         "clock": var.owner.clock.name,
+                        "compact_always": False,
                     }
+        # The compacted (reference-layout) list of a step is only built when somebody reads it:
+        # pathways with a delay (decided at run time from the delays), and -- decided here --
+        # order-dependent synaptic code, which walks the compact list of the current step.
+        for codeobj in self.code_objects.values():
+            info = self._b200_info.get(codeobj.name)
+            if info is None or info["template"] != "synapses":
+                continue
+            if self._b200_access.get(codeobj.name, {}).get("serial"):
+                pathway = info["template_kwds"]["pathway"]
+                name = self.arrays[pathway.source.variables[pathway.eventspace_name]]
+                if name in spaces:
+                    spaces[name]["compact_always"] = True
         return [spaces[k] for k in sorted(spaces)]
 
     def _summed_updaters(self):

@@ -168,6 +168,7 @@ void _b200_upload()
     _A_host._world = st.world;
     {% for es in b200_eventspaces %}
     _b200_es{{es.name}}.id = {{loop.index}};
+    _b200_es{{es.name}}.compact_always = {{ 'true' if es.compact_always else 'false' }};
     _b200_es{{es.name}}.ensure({{es.size - 1}}, _b200_grid_size(), _now.{{es.clock}}.timestep);
     {% endfor %}
     {% for es in b200_eventspaces %}

@@ -49,10 +49,20 @@
     const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
     const int _nwarps = _ctx.nb * b200::kWarps;
     unsigned long long _nev = 0ULL;
+    // work counter of the NEXT step (see "heavy steps" below): zeroed by one thread every step;
+    // the end-of-step barrier orders it before its first use
+    if (_ctx.bid == 0 && threadIdx.x == 0) _pw.tickets[(_b200_timestep + 1) & 1] = 0u;
+    // parameters of the first 32 delay bins, one per lane (in flight while the view is built)
+    int _bdelay0 = 0, _blr0 = 1;
+    if (_lane < _pw.nbins)
+    {
+        _bdelay0 = __ldg(_pw.bin_delay + _lane);
+        _blr0 = (__ldg(_pw.bin_maxlen + _lane) + 62) >> 5;
+    }
     // The list of the current step (delay 0) is read from the thresholder's segments
     b200::SpikeView _view;
     _view.total = 0;
-    if (_pw.nbins > 0 && _pw.bin_delay[0] == 0)
+    if (_pw.has_delay0)
         _view = b200::view_build(_es, _b200_timestep, _ctx, false, _A._ctrl);
     // Work = 128-byte lines of the packed index stream.  Every (delay bin, spike of that bin's
     // step) row is padded to the bin's longest row (`_lr` lines of 32 slots, on 32-slot boundaries:
@@ -69,8 +79,8 @@
         const int32_t* _bspk = 0;
         if (_mybin < _pw.nbins)
         {
-            _bdelay = _pw.bin_delay[_mybin];
-            _blr = (_pw.bin_maxlen[_mybin] + 62) >> 5;
+            _bdelay = _g0 == 0 ? _bdelay0 : __ldg(_pw.bin_delay + _mybin);
+            _blr = _g0 == 0 ? _blr0 : ((__ldg(_pw.bin_maxlen + _mybin) + 62) >> 5);
             if (_blr < 1) _blr = 1;
             if (_bdelay == 0)
                 _bn = _view.total;
@@ -93,10 +103,31 @@
         if (_nlines <= 0) continue;
         // (32-bit divisions whenever the numbers allow: ~10x cheaper)
         const bool _small = _nlines * (long long)_nwarps < 0xffffffffLL;
-        long long _a = _small ? (long long)(((unsigned int)_gwarp * (unsigned int)_nlines) / (unsigned int)_nwarps)
-                              : ((long long)_gwarp * _nlines) / _nwarps;
-        const long long _b = _small ? (long long)(((unsigned int)(_gwarp + 1) * (unsigned int)_nlines) / (unsigned int)_nwarps)
-                                    : ((long long)(_gwarp + 1) * _nlines) / _nwarps;
+        // Heavy steps (>= 64 lines per warp, one bin group): the lines are handed out in tickets
+        // of 32 lines from a device counter instead of fixed shares, so that CTAs that see a
+        // slower memory system (far L2 partition) simply take fewer tickets.  The counter of the
+        // NEXT step is zeroed above.
+        const bool _dyn = _pw.nbins <= 32 && _nlines >= 64LL * _nwarps;
+        unsigned int* _tickets = _pw.tickets + (_b200_timestep & 1);
+        long long _a, _b;
+        unsigned int _next_ticket = 0u;
+        if (_dyn)
+        {
+            unsigned int _t0 = 0u;
+            if (_lane == 0) { _t0 = atomicAdd(_tickets, 1u); _next_ticket = atomicAdd(_tickets, 1u); }
+            _t0 = __shfl_sync(0xffffffffu, _t0, 0);
+            _a = 32LL * _t0;
+            _b = min(_a + 32, _nlines);
+        }
+        else
+        {
+            _a = _small ? (long long)(((unsigned int)_gwarp * (unsigned int)_nlines) / (unsigned int)_nwarps)
+                        : ((long long)_gwarp * _nlines) / _nwarps;
+            _b = _small ? (long long)(((unsigned int)(_gwarp + 1) * (unsigned int)_nlines) / (unsigned int)_nwarps)
+                        : ((long long)(_gwarp + 1) * _nlines) / _nwarps;
+        }
+        for (;;)
+        {
         while (_a < _b)
         {
             const int _L = 31 - __clz(__ballot_sync(0xffffffffu, _bexcl <= _a));
@@ -144,6 +175,14 @@
                     {{vector_code|autoindent}}
                 }
             }
+        }
+        if (!_dyn) break;
+        // next ticket (requested one ticket ahead: its round trip overlapped the work above)
+        const unsigned int _t1 = __shfl_sync(0xffffffffu, _next_ticket, 0);
+        _a = 32LL * _t1;
+        if (_a >= _nlines) break;
+        _b = min(_a + 32, _nlines);
+        if (_lane == 0) _next_ticket = atomicAdd(_tickets, 1u);
         }
     }
     // delivered synaptic events (the benchmark metric): one atomic per warp per step

@@ -34,6 +34,10 @@ CASES = {
     "stdp_1000": ("stdp", dict(N=1000, duration=0.2)),
     "synapses_only": ("synapses_only", dict(N=2000, p=0.2, rate_hz=100.0, duration=0.005)),
     "synapses_only_delay": ("synapses_only", dict(N=2000, p=0.2, rate_hz=100.0, duration=0.005, delay_steps=3)),
+    # heavy steps: > 64 lines of 32 synapses per warp of the grid -> the ticket-based (dynamic)
+    # distribution of the propagation kernel
+    "synapses_only_heavy": ("synapses_only", dict(N=60000, p=0.3, rate_hz=100.0, duration=0.0005)),
+    "ragged": ("ragged", dict(N=600, duration=0.03)),
     "spikegen": ("spikegen", dict(N=200, n_spikes=3000, duration=0.05)),
     "spikegen_period": ("spikegen", dict(N=200, n_spikes=600, duration=0.05, period_ms=10.0)),
     "gapjunction": ("gapjunction", dict(N=300, p=0.1, duration=0.05)),

@@ -297,9 +297,39 @@ def poisson_drive(b, N=2000, duration=0.1, seed=31):
     return objs
 
 
+def ragged(b, N=600, duration=0.03, seed=17):
+    """Stress of the propagation kernel's work distribution (templates/synapses.cu): CSR rows of
+    very different lengths (0 ... N/2, `j <= i`), 45 distinct delays (two groups of 32 delay bins,
+    delay 0 included), subgroup sources AND targets (absolute indices with offsets,
+    synapses_create_generator.cpp:38,184), per-synapse weights, on_pre and on_post pathways.
+    All increments are multiples of 1/8, so every sum is exact in any order."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """dv/dt = rate : 1
+                            rate : Hz
+                            x : 1
+                            y : 1""", threshold="v >= 1", reset="v = 0", method="euler", name="rg_neurons")
+    G.rate = "(50 + (i * 37) % 400) * Hz"
+    G.v = "((i * 13) % 16) / 16.0"
+    src = G[N // 4: 3 * N // 4]
+    tgt = G[N // 8: 5 * N // 8]
+    S = b.Synapses(src, tgt, "w : 1", on_pre="x_post += w", on_post="y_pre += 0.125\nw += 0.25",
+                   name="rg_S")
+    S.connect(condition="j <= i")
+    S.w = "((i + 3 * j) % 8) * 0.125"
+    S.pre.delay = "((i * 7 + j) % 45) * 0.1*ms"
+    S.post.delay = "((i + j) % 3) * 0.1*ms"
+    objs = dict(G=G, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="rg_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "x"), ("G", "y"), ("S", "w")]
+    return objs
+
+
 MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=synapses_only,
               spikegen=spikegen, gapjunction=gapjunction, timedarray=timedarray,
-              poisson_drive=poisson_drive)
+              poisson_drive=poisson_drive, ragged=ragged)
 
 
 def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):

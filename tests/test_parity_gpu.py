@@ -36,6 +36,9 @@ def _check(case, res, exact_state):
     ("brunel_hetero", True),
     ("synapses_only", True),
     ("synapses_only_delay", True),
+    ("synapses_only_heavy", True),
+    # ragged CSR rows, 45 delay bins (two bin groups), subgroup offsets, on_pre + on_post
+    ("ragged", True),
     # exponential_euler evaluates exp/expm1 per neuron on the device (CUDA libm, <= 1-2 ulp from
     # glibc): spikes must still be identical over this horizon, state within rtol 1e-9
     ("cobahh_1000", False),
