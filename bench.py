@@ -38,6 +38,12 @@ WORKLOADS = {
     "cuba_4k": ("cuba", dict(N=4000, p=0.02), 58.0, 20.0),
     "cuba_256k": ("cuba", dict(N=256000, p=80.0 / 256000), 58.0, 20.0),
     "brunel_100k": ("brunel", dict(N_E=80000, epsilon=0.01, deterministic=True), 33.0, 20.0),
+    # BASELINE configs[2] per GPU: 125k neurons x 1000 synapses each; `--gpus 8` = 1M neurons / 1B
+    # synapses, heterogeneous delays 1..20 steps, partitioned by postsynaptic neuron
+    "brunel_125k": ("brunel", dict(N_E=100000, epsilon=0.008, deterministic=True), 33.0, 20.0),
+    # BASELINE configs[3]: Song-Abbott STDP, 100k plastic synapses onto one neuron (on_pre 84 B,
+    # on_post 68 B per event; regular-firing inputs instead of Poisson so that it is deterministic)
+    "stdp_100k": ("stdp", dict(N=100000), 0.0, 84.0),
     # propagation stress (brian2/tests/features/speed.py:263-326 SynapsesOnly): every source spikes
     # every step, `w += 1.0` per event -> the step is synaptic propagation only (20 B/event)
     "synapses_only_sparse": ("synapses_only", dict(N=100000, p=0.2, rate_hz=10.0), 0.0, 20.0),
@@ -48,7 +54,7 @@ WORKLOADS = {
 
 # simulation timesteps (dt = 0.1 ms) of one bench step = one run() call
 DEFAULT_SIM_STEPS = {"cobahh_256k": 4000, "cuba_256k": 4000, "cuba_4k": 10000, "cobahh_4k": 10000,
-                     "brunel_100k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
+                     "brunel_100k": 2000, "brunel_125k": 1000, "stdp_100k": 5000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
                      "synapses_only_highrate": 500}
 
 
@@ -183,21 +189,30 @@ def _scaled(kwds, scale):
 
 
 def _outdegree_events(b, objs, t_from):
-    """Synaptic events in [t_from, end): sum over recorded spikes of the out-degree of the
-    spiking neuron over every pathway listening to it."""
+    """Synaptic events in [t_from, end): for every pathway (on_pre and on_post) the sum over the
+    recorded spikes of its event source of the number of synapses attached to the spiking
+    neuron.  Needs a SpikeMonitor on every group that drives a pathway."""
     import numpy as np
 
-    spikes = objs["spikes"]
-    i = np.asarray(spikes.i[:])
-    t = np.asarray(spikes.t_[:])
-    sel = i[t >= t_from - 1e-12]
-    n = len(objs["spikes"].source)
-    out = np.zeros(n, dtype=np.int64)
+    mons = {m.source.name: m for m in objs.values() if isinstance(m, b.SpikeMonitor)}
+    total, nspikes = 0.0, 0
     for obj in objs.values():
-        if isinstance(obj, b.Synapses):
-            pre = np.asarray(obj.i[:]) + getattr(obj.source, "start", 0)
-            out += np.bincount(pre, minlength=n)
-    return float(out[sel].sum()), int(len(sel))
+        if not isinstance(obj, b.Synapses):
+            continue
+        for path in obj._pathways:
+            grp = path.source
+            parent = getattr(grp, "source", grp)
+            ends = np.asarray(obj.i[:] if path.prepost == "pre" else obj.j[:])
+            if grp.name in mons:        # monitor on the (sub)group itself: relative indices
+                mon, deg = mons[grp.name], np.bincount(ends, minlength=len(grp))
+            else:
+                mon = mons[parent.name]
+                deg = np.bincount(ends + getattr(grp, "start", 0), minlength=len(parent))
+            i, t = np.asarray(mon.i[:]), np.asarray(mon.t_[:])
+            sel = i[t >= t_from - 1e-12]
+            total += float(deg[sel].sum())
+            nspikes += int(len(sel))
+    return total, nspikes
 
 
 def run_b200(args, rank, world):

@@ -310,11 +310,19 @@ __device__ int* view_storage(long long** tag) {
     *tag = &s_tag;
     return s_pref;
 }
+// Per-CTA memo for the state monitors of a launch: 1 = none of the recorded elements belongs to
+// this CTA (the code object returns at once in every later step), 0 = some do, -1 = unknown.
+constexpr int kMonitorMemo = 8;
+__device__ __forceinline__ int* monitor_memo() {
+    __shared__ int s_memo[kMonitorMemo];
+    return s_memo;
+}
 // to be called once at kernel start
 __device__ __forceinline__ void view_reset() {
     long long* tag;
     view_storage(&tag);
     if (threadIdx.x == 0) *tag = 0;
+    if (threadIdx.x < kMonitorMemo) monitor_memo()[threadIdx.x] = -1;
     slice_cache_reset();
     __syncthreads();
 }

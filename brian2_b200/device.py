@@ -229,6 +229,10 @@ class B200Device(CPPStandaloneDevice):
 
                 src = owner.source
                 template_kwds["b200_source_size"] = int(len(src)) if isinstance(src, NeuronGroup) else None
+                # slot of the per-CTA "records nothing here" memo (csrc/b200_runtime.cuh)
+                self._b200_memo_slots = getattr(self, "_b200_memo_slots", {})
+                slot = self._b200_memo_slots.setdefault(owner.name, len(self._b200_memo_slots) % 8)
+                template_kwds["b200_memo_slot"] = slot
         # seen by the CUDA generator while it translates this code object (pathway direction)
         self._b200_current_template_kwds = template_kwds
         codeobj = super().code_object(

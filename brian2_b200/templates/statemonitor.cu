@@ -8,6 +8,25 @@
    the neurons it owns and the host merges the columns after the run. #}
 {% extends 'common_group.cu' %}
 {% block maincode %}
+    {% if b200_source_size is not none %}
+    // Does this CTA own any recorded element?  Decided once per launch (the recorded indices do
+    // not change inside a run); CTAs that own none leave at once in every later step.
+    const b200::Slice _mine = b200::owned_cta((int64_t){{b200_source_size}}, _ctx);
+    int* _memo = b200::monitor_memo() + {{b200_memo_slot}};
+    if (*_memo < 0)
+    {
+        int _any = 0;
+        for (int _i = threadIdx.x; _i < (int)_num_indices; _i += b200::kBlock)
+        {
+            const int _idx = {{_indices}}[_i];
+            if (_idx >= _mine.lo && _idx < _mine.hi) _any = 1;
+        }
+        _any = __syncthreads_or(_any);
+        if (threadIdx.x == 0) *_memo = _any ? 0 : 1;
+        __syncthreads();
+    }
+    if (*_memo == 1 && _ctx.bid != 0) return;
+    {% endif %}
     const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
     long long* _monN = _A._monN_{{owner.name}};
     const long long _row = _monN[_par];
@@ -20,7 +39,6 @@
     // scalar code
     {{scalar_code|autoindent}}
     {% if b200_source_size is not none %}
-    const b200::Slice _mine = b200::owned_cta((int64_t){{b200_source_size}}, _ctx);
     for (int _i = threadIdx.x; _i < (int)_num_indices; _i += b200::kBlock)
     {
         const int _idx = {{_indices}}[_i];

@@ -101,6 +101,15 @@
         const long long _bexcl = _bincl - _blines;
         const long long _nlines = __shfl_sync(0xffffffffu, _bincl, 31);
         if (_nlines <= 0) continue;
+        int _rincl = _bn;                       // rows (spikes) of the bins, same scan
+        #pragma unroll
+        for (int _o = 1; _o < 32; _o <<= 1)
+        {
+            const int _t = __shfl_up_sync(0xffffffffu, _rincl, _o);
+            if (_lane >= _o) _rincl += _t;
+        }
+        const int _rexcl = _rincl - _bn;
+        const int _nrows = __shfl_sync(0xffffffffu, _rincl, 31);
         // (32-bit divisions whenever the numbers allow: ~10x cheaper)
         const bool _small = _nlines * (long long)_nwarps < 0xffffffffLL;
         // Heavy steps (>= 64 lines per warp, one bin group): the lines are handed out in tickets
@@ -118,6 +127,25 @@
             _t0 = __shfl_sync(0xffffffffu, _t0, 0);
             _a = 32LL * _t0;
             _b = min(_a + 32, _nlines);
+        }
+        else if (_nrows <= _nwarps)
+        {
+            // Light step (fewer rows than warps): every warp works on (a part of) ONE row, so the
+            // step pays one chain of dependent loads (spike id -> row pointers -> indices), not one
+            // per row of a share; `_k` neighbouring warps split the lines of a row.
+            const int _k = _nwarps / _nrows;
+            const int _r = _gwarp / _k, _part = _gwarp - _r * _k;
+            _a = _b = 0;
+            if (_r < _nrows)
+            {
+                const int _L = 31 - __clz(__ballot_sync(0xffffffffu, _rexcl <= _r));
+                const int _s = _r - __shfl_sync(0xffffffffu, _rexcl, _L);
+                const int _lr = __shfl_sync(0xffffffffu, _blr, _L);
+                const int _per = (_lr + _k - 1) / _k;
+                const int _lo = min(_lr, _part * _per), _hi = min(_lr, _lo + _per);
+                _a = __shfl_sync(0xffffffffu, _bexcl, _L) + (long long)_s * _lr + _lo;
+                _b = _a + (_hi - _lo);
+            }
         }
         else
         {
