@@ -83,6 +83,9 @@ void Network::run(const double duration, void (*report_func)(const double, const
     const long long _steps_before = Network::_b200_steps_run;
     const double _upload_before = b200::state().upload_seconds;
     B200_CUDA(cudaDeviceSynchronize());
+    // several GPUs: the ranks enter the loop together (their uploads take different times, and a
+    // rank whose peer starts late would spin on the peer's first spike list inside the timed loop)
+    b200::host_barrier();
     B200_CUDA(cudaEventRecord(_ev_start, b200::state().stream));
     hrc::time_point start = hrc::now(), current;
     const double _t0_unix = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
