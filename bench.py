@@ -311,7 +311,19 @@ def _barrier(world):
 
     if not _PG["init"]:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        # NCCL announces its version on stdout when the first communicator is created: keep
+        # stdout for the one JSON line of the contract
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl")
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         _PG["init"] = True
     dist.barrier()
     torch.cuda.synchronize()

@@ -479,6 +479,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
         kwds["b200_scalar_members"] = scal_members
         kwds["b200_serial"] = serial
         kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)
+        kwds["b200_gather_unroll"] = 2 if kwds["b200_unroll"] > 1 else 1
         # remembered by the device for the barrier analysis of the persistent kernel
         access["serial"] = serial
         self.device._b200_access[self.name] = access

@@ -48,7 +48,8 @@
     const int _lane = threadIdx.x & 31;
     const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
     const int _nwarps = _ctx.nb * b200::kWarps;
-    unsigned long long _nev = 0ULL;
+    unsigned long long _nev = 0ULL;        // events counted by the whole warp (same value in all lanes)
+    unsigned long long _nev_lane = 0ULL;   // events counted lane by lane (gather mode)
     // work counter of the NEXT step (see "heavy steps" below): zeroed by one thread every step;
     // the end-of-step barrier orders it before its first use
     if (_ctx.bid == 0 && threadIdx.x == 0) _pw.tickets[(_b200_timestep + 1) & 1] = 0u;
@@ -118,6 +119,94 @@
         // NEXT step is zeroed above.
         const bool _dyn = _pw.nbins <= 32 && _nlines >= 64LL * _nwarps;
         unsigned int* _tickets = _pw.tickets + (_b200_timestep & 1);
+        // Many short rows (more rows than warps, every row <= 4 lines: sharded Brunel, COBAHH at
+        // high rates): GATHER mode.  A warp takes an equal share of the ROWS, 32 at a time: lane l
+        // fetches the spike id and the row pointers of row l (32 chains of dependent loads in
+        // flight together instead of one after the other), a warp scan of the row lengths turns
+        // the 32 rows into one dense run of slots, and every lane then delivers one slot per
+        // pass (all lanes busy however short the rows are; a slot finds its row with a 5-step
+        // search over the scanned lengths by shuffles).
+        int _maxlr = _mybin < _pw.nbins ? _blr : 0;
+        #pragma unroll
+        for (int _o = 16; _o > 0; _o >>= 1) _maxlr = max(_maxlr, __shfl_xor_sync(0xffffffffu, _maxlr, _o));
+        if (!_dyn && _nrows > _nwarps && _maxlr <= 4)
+        {
+            const int _ra = (int)(((long long)_gwarp * _nrows) / _nwarps);
+            const int _rb = (int)(((long long)(_gwarp + 1) * _nrows) / _nwarps);
+            for (int _r0 = _ra; _r0 < _rb; _r0 += 32)
+            {
+                const bool _rv = _r0 + _lane < _rb;
+                const int _r = _rv ? _r0 + _lane : _ra;
+                int _blo = 0, _bhi = 32;             // bin of row _r: last bin with _rexcl <= _r
+                #pragma unroll
+                for (int _i = 0; _i < 5; ++_i)
+                {
+                    const int _mid = (_blo + _bhi) >> 1;
+                    if (__shfl_sync(0xffffffffu, _rexcl, _mid) <= _r) _blo = _mid; else _bhi = _mid;
+                }
+                const int _s = _r - __shfl_sync(0xffffffffu, _rexcl, _blo);
+                const int _delay = __shfl_sync(0xffffffffu, _bdelay, _blo);
+                const int32_t* _spk = (const int32_t*)__shfl_sync(0xffffffffu, (unsigned long long)_bspk, _blo);
+                int _len = 0, _rbeg = 0, _srcabs = 0;
+                if (_rv)
+                {
+                    const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
+                    if (_src >= 0 && _src < _pw.nsrc)
+                    {
+                        const int* _rp = _pw.rowptr + (size_t)(_g0 + _blo) * (_pw.nsrc + 1);
+                        _rbeg = _rp[_src];
+                        _len = _rp[_src + 1] - _rbeg;
+                        _srcabs = _src + _pw.src_start;
+                    }
+                }
+                _nev_lane += (unsigned long long)_len;
+                int _lincl = _len;
+                #pragma unroll
+                for (int _o = 1; _o < 32; _o <<= 1)
+                {
+                    const int _t = __shfl_up_sync(0xffffffffu, _lincl, _o);
+                    if (_lane >= _o) _lincl += _t;
+                }
+                const int _lexcl = _lincl - _len;
+                const int _nslots = __shfl_sync(0xffffffffu, _lincl, 31);
+                for (int _base = 0; _base < _nslots; _base += 32 * {{b200_gather_unroll}})
+                {
+                    int _b200_tg[{{b200_gather_unroll}}], _b200_sy[{{b200_gather_unroll}}], _b200_sa[{{b200_gather_unroll}}];
+                    #pragma unroll
+                    for (int _u = 0; _u < {{b200_gather_unroll}}; ++_u)
+                    {
+                        const int _slot = _base + 32 * _u + _lane;
+                        const bool _sv = _slot < _nslots;
+                        const int _sl = _sv ? _slot : 0;
+                        int _jlo = 0, _jhi = 32;     // row of the slot: last row with _lexcl <= _sl
+                        #pragma unroll
+                        for (int _i = 0; _i < 5; ++_i)
+                        {
+                            const int _mid = (_jlo + _jhi) >> 1;
+                            if (__shfl_sync(0xffffffffu, _lexcl, _mid) <= _sl) _jlo = _mid; else _jhi = _mid;
+                        }
+                        const int _k = __shfl_sync(0xffffffffu, _rbeg, _jlo) + _sl - __shfl_sync(0xffffffffu, _lexcl, _jlo);
+                        _b200_sa[_u] = __shfl_sync(0xffffffffu, _srcabs, _jlo);
+                        _b200_tg[_u] = _sv ? __ldg(_pw.csr_target + _k) : -1;
+                        _b200_sy[_u] = (_sv && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
+                    }
+                    #pragma unroll
+                    for (int _u = 0; _u < {{b200_gather_unroll}}; ++_u)
+                    {
+                        if (_base + 32 * _u + _lane >= _nslots) break;
+                        const int _idx = _b200_sy[_u];
+                        const int _b200_tgt_idx = _b200_tg[_u];
+                        const int _b200_src_idx = _b200_sa[_u];
+                        const int _vectorisation_idx = _idx;
+                        {% if b200_uses_rng %}
+                        b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
+                        {% endif %}
+                        {{vector_code|autoindent}}
+                    }
+                }
+            }
+            continue;
+        }
         long long _a, _b;
         unsigned int _next_ticket = 0u;
         if (_dyn)
@@ -214,6 +303,9 @@
         }
     }
     // delivered synaptic events (the benchmark metric): one atomic per warp per step
+    #pragma unroll
+    for (int _o = 16; _o > 0; _o >>= 1) _nev_lane += __shfl_xor_sync(0xffffffffu, _nev_lane, _o);
+    _nev += _nev_lane;
     if (_lane == 0 && _nev) atomicAdd(_pw.events, _nev);
     {% endif %}
 {% endblock %}

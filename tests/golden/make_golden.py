@@ -37,6 +37,10 @@ CASES = {
     # heavy steps: > 64 lines of 32 synapses per warp of the grid -> the ticket-based (dynamic)
     # distribution of the propagation kernel
     "synapses_only_heavy": ("synapses_only", dict(N=60000, p=0.3, rate_hz=100.0, duration=0.0005)),
+    # many short rows per step (6000 spiking sources x ~20 synapses, 5 delay bins): the gather mode
+    # of the propagation kernel
+    "synapses_only_short": ("synapses_only", dict(N=1000, p=0.02, rate_hz=60000.0, duration=0.002,
+                                                   hetero_bins=5)),
     "ragged": ("ragged", dict(N=600, duration=0.03)),
     "spikegen": ("spikegen", dict(N=200, n_spikes=3000, duration=0.05)),
     "spikegen_period": ("spikegen", dict(N=200, n_spikes=600, duration=0.05, period_ms=10.0)),

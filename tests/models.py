@@ -187,7 +187,7 @@ def stdp(b, N=1000, duration=0.2, seed=99, raster_seed=7, monitor=True):
     return objs
 
 
-def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, delay_steps=0):
+def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, delay_steps=0, hetero_bins=0):
     """Propagation stress test (brian2/tests/features/speed.py:263-326 `SynapsesOnly`): M source
     neurons that spike every step, N targets, `w += 1.0` per event."""
     b.seed(seed)
@@ -199,6 +199,8 @@ def synapses_only(b, N=20000, p=0.2, rate_hz=100.0, duration=0.01, seed=11, dela
     S.connect(True, p=p)
     if delay_steps:
         S.delay = delay_steps * b.defaultclock.dt
+    if hetero_bins:     # delays 0 .. hetero_bins-1 steps, by target
+        S.delay = f"(j % {int(hetero_bins)}) * 0.1*ms"
     objs = dict(G=G, H=H, S=S)
     objs["net"] = b.Network(G, H, S)
     objs["duration"] = duration

@@ -37,6 +37,7 @@ def _check(case, res, exact_state):
     ("synapses_only", True),
     ("synapses_only_delay", True),
     ("synapses_only_heavy", True),
+    ("synapses_only_short", True),
     # ragged CSR rows, 45 delay bins (two bin groups), subgroup offsets, on_pre + on_post
     ("ragged", True),
     # exponential_euler evaluates exp/expm1 per neuron on the device (CUDA libm, <= 1-2 ulp from
@@ -124,6 +125,7 @@ def test_multi_gpu_sharded_parity():
     script = os.path.join(os.path.dirname(__file__), "run_multigpu_case.py")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", script,
-           "cuba_1000", "brunel_hetero", "brunel_homog", "cobahh_1000", "stdp_1000", "synapses_only_delay"]
+           "cuba_1000", "brunel_hetero", "brunel_homog", "cobahh_1000", "stdp_1000", "synapses_only_delay",
+           "synapses_only_short", "synapses_only_heavy"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     assert "MULTIGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
