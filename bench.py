@@ -44,6 +44,10 @@ WORKLOADS = {
     # BASELINE configs[3]: Song-Abbott STDP, 100k plastic synapses onto one neuron (on_pre 84 B,
     # on_post 68 B per event; regular-firing inputs instead of Poisson so that it is deterministic)
     "stdp_100k": ("stdp", dict(N=100000), 0.0, 84.0),
+    # BASELINE configs[4]: Potjans-Diesmann microcircuit, 77 169 neurons / ~3e8 synapses with
+    # per-synapse weights and delays, DC background (deterministic); 50 B/neuron-step, 28 B/event
+    "potjans_77k": ("potjans", dict(scale=1.0), 50.0, 28.0),
+    "potjans_8k": ("potjans", dict(scale=0.1), 50.0, 28.0),
     # propagation stress (brian2/tests/features/speed.py:263-326 SynapsesOnly): every source spikes
     # every step, `w += 1.0` per event -> the step is synaptic propagation only (20 B/event)
     "synapses_only_sparse": ("synapses_only", dict(N=100000, p=0.2, rate_hz=10.0), 0.0, 20.0),
@@ -54,12 +58,12 @@ WORKLOADS = {
 
 # simulation timesteps (dt = 0.1 ms) of one bench step = one run() call
 DEFAULT_SIM_STEPS = {"cobahh_256k": 4000, "cuba_256k": 4000, "cuba_4k": 10000, "cobahh_4k": 10000,
-                     "brunel_100k": 2000, "brunel_125k": 1000, "stdp_100k": 5000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
+                     "brunel_100k": 2000, "brunel_125k": 1000, "stdp_100k": 5000, "potjans_77k": 1000, "potjans_8k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
                      "synapses_only_highrate": 500}
 
 
 def _n_neurons(objs):
-    for key in ("P", "neurons", "H"):
+    for key in ("P", "neurons", "H", "G"):
         if key in objs:
             return len(objs[key])
     return 0

@@ -135,6 +135,26 @@ inline void download_vector(std::vector<T>& host, const T* dev, size_t n) {
     if (n && dev) B200_CUDA(cudaMemcpy(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
     state().d2h_bytes += n * sizeof(T);
 }
+// Monitor records (append-only, read-only for the user): host and device copies agree on the
+// first `synced` elements after every download, so a later run() neither sends them to the
+// device again nor fetches them a second time -- only the records of the run that just ended
+// cross PCIe.
+template <typename T>
+inline void upload_records(T*& dev, size_t& cap, size_t& n, const std::vector<T>& host, size_t min_cap,
+                           size_t& synced) {
+    if (dev && host.size() == synced && n == synced && cap >= std::max(host.size(), min_cap)) return;
+    upload_vector(dev, cap, n, host, min_cap);
+    synced = host.size();
+}
+template <typename T>
+inline void download_records(std::vector<T>& host, const T* dev, size_t n, size_t& synced) {
+    const size_t from = (host.size() == synced && n >= synced) ? synced : 0;
+    host.resize(n);
+    if (n > from && dev)
+        B200_CUDA(cudaMemcpy(host.data() + from, dev + from, (n - from) * sizeof(T), cudaMemcpyDeviceToHost));
+    state().d2h_bytes += (n - from) * sizeof(T);
+    synced = n;
+}
 // grow a device append buffer, preserving the first `used` elements
 template <typename T>
 inline void grow_buffer(T*& dev, size_t& cap, size_t used, size_t new_cap) {

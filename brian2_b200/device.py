@@ -590,11 +590,29 @@ class B200Device(CPPStandaloneDevice):
     def _array_table(self, monitors):
         """Description of every array for the device array table template."""
         used, written = set(), set()
+        import re as _re
+
+        def referenced(var, code):
+            """Does the generated device code touch the array (beyond declaring a pointer to it)?
+            Only asked for arrays that are constant during runs: the synaptic index arrays
+            `_synaptic_pre/_post` are in every synaptic code object's variables, but the CUDA
+            templates take both ends of a synapse from the CSR, so these (large) arrays need
+            not be copied to the device at all unless user code reads `i`/`j`."""
+            name = _re.escape(self.arrays[var])
+            return bool(_re.search(rf"_ptr{name}\s*\[|_A\.{name}\b(?!\s*;)", code))
+
         for codeobj in self.code_objects.values():
             if not self.is_device_codeobj(codeobj):
                 continue
+            code = None
             for var in codeobj.variables.values():
                 if isinstance(var, ArrayVariable):
+                    if (var.constant and var.read_only and var in self.dynamic_arrays
+                            and self._b200_info[codeobj.name]["template"] == "synapses"):
+                        if code is None:
+                            code = str(codeobj.code.cpp_file)
+                        if not referenced(var, code):
+                            continue
                     used.add(var)
             if self._b200_info[codeobj.name]["template"] == "synapses_push_spikes":
                 continue

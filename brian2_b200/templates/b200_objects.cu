@@ -100,6 +100,12 @@ b200::TargetIndex _b200_sv_{{sv}};
 static long long _monN_ub_{{mon.name}} = 0;
 {% endfor %}
 static bool _b200_first_upload = true;
+// monitor records: number of leading elements identical on host and device (see upload_records)
+{% for a in b200_arrays %}
+{% if a.used and a.kind == 'dynamic1d' and a.monitor %}
+static size_t _b200_synced{{a.name}} = 0;
+{% endif %}
+{% endfor %}
 
 _B200Clocks _b200_clocks_now()
 {
@@ -136,6 +142,8 @@ void _b200_upload()
     {% if a.used %}
     {% if a.kind == 'static' %}
     b200::upload_array(_A_host.{{a.name}}, brian::{{a.name}}, {{a.size}});
+    {% elif a.kind == 'dynamic1d' and a.monitor %}
+    b200::upload_records(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}}, _b200_synced{{a.name}});
     {% elif a.kind == 'dynamic1d' %}
     b200::upload_vector(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}});
     {% elif a.kind == 'dynamic2d' %}
@@ -199,6 +207,7 @@ void _b200_upload()
 
 // Guarantee that every monitor can record `steps` more steps (exact == true: the true entry
 // counts are read back first; false: cheap host-side upper bounds are used).
+static long long _b200_steps_prepared = 0;   // steps of the earlier launches (event-rate estimate)
 void _b200_prepare_steps(long long steps, bool exact)
 {
     bool changed = false;
@@ -213,6 +222,11 @@ void _b200_prepare_steps(long long steps, bool exact)
         // worst case one entry per source neuron per step; the kernel raises `overflow` when
         // fewer than one step's worst case of slots is free
         long long _need = _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * (exact ? 2 : 1);
+        // a launch of `steps` steps at the event rate seen so far (x1.5) should fit without
+        // interrupting the persistent kernel for a buffer growth
+        if (exact && _b200_steps_prepared > 0 && steps > 1)
+            _need = std::max(_need, _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * 2 +
+                                    (long long)(1.5 * (double)_monN_ub_{{mon.name}} / (double)_b200_steps_prepared * (double)steps));
         {% else %}
         long long _need = _monN_ub_{{mon.name}} + steps;
         {% endif %}
@@ -255,6 +269,7 @@ void _b200_prepare_steps(long long steps, bool exact)
         {% endif %}
     }
     {% endfor %}
+    if (exact) _b200_steps_prepared += steps;
     if (changed) _b200_sync_constants();
 }
 
@@ -284,7 +299,8 @@ void _b200_download()
     b200::download_array(brian::{{a.name}}, _A_host.{{a.name}}, {{a.size}});
     {% elif a.kind == 'dynamic1d' %}
     {% if a.monitor %}
-    b200::download_vector(brian::{{a.dyn_name}}, _A_host.{{a.name}}, (size_t)_monN_{{a.monitor}});
+    b200::download_records(brian::{{a.dyn_name}}, _A_host.{{a.name}}, (size_t)_monN_{{a.monitor}}, _b200_synced{{a.name}});
+    _A_host._n{{a.name}} = (size_t)_monN_{{a.monitor}};
     {% else %}
     b200::download_vector(brian::{{a.dyn_name}}, _A_host.{{a.name}}, _A_host._n{{a.name}});
     {% endif %}

@@ -41,6 +41,8 @@ CASES = {
     # of the propagation kernel
     "synapses_only_short": ("synapses_only", dict(N=1000, p=0.02, rate_hz=60000.0, duration=0.002,
                                                    hetero_bins=5)),
+    # Potjans-Diesmann microcircuit at 1 % of the neurons (in-degrees preserved), DC background
+    "potjans_small": ("potjans", dict(scale=0.01, duration=0.05)),
     "ragged": ("ragged", dict(N=600, duration=0.03)),
     "spikegen": ("spikegen", dict(N=200, n_spikes=3000, duration=0.05)),
     "spikegen_period": ("spikegen", dict(N=200, n_spikes=600, duration=0.05, period_ms=10.0)),

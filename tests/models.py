@@ -329,9 +329,93 @@ def ragged(b, N=600, duration=0.03, seed=17):
     return objs
 
 
+# Potjans & Diesmann (2014) cortical microcircuit: population sizes, connection probabilities
+# C[target][source], external in-degrees (published parameter tables; not in the reference repo)
+PD_NAMES = ["L23E", "L23I", "L4E", "L4I", "L5E", "L5I", "L6E", "L6I"]
+PD_SIZES = [20683, 5834, 21915, 5479, 4850, 1065, 14395, 2948]
+PD_CONN = [[0.1009, 0.1689, 0.0437, 0.0818, 0.0323, 0.0, 0.0076, 0.0],
+           [0.1346, 0.1371, 0.0316, 0.0515, 0.0755, 0.0, 0.0042, 0.0],
+           [0.0077, 0.0059, 0.0497, 0.1350, 0.0067, 0.0003, 0.0453, 0.0],
+           [0.0691, 0.0029, 0.0794, 0.1597, 0.0033, 0.0, 0.1057, 0.0],
+           [0.1004, 0.0622, 0.0505, 0.0057, 0.0831, 0.3726, 0.0204, 0.0],
+           [0.0548, 0.0269, 0.0257, 0.0022, 0.0600, 0.3158, 0.0086, 0.0],
+           [0.0156, 0.0066, 0.0211, 0.0166, 0.0572, 0.0197, 0.0396, 0.2252],
+           [0.0364, 0.0010, 0.0034, 0.0005, 0.0277, 0.0080, 0.0658, 0.1443]]
+PD_KEXT = [1600, 1500, 2100, 1900, 2000, 1900, 2900, 2100]
+
+
+def potjans(b, scale=0.02, duration=0.05, seed=55, poisson=False, monitor=True):
+    """Potjans-Diesmann microcircuit (BASELINE.json configs[4]): 8 populations of LIF neurons with
+    exponential current synapses, fixed total number of synapses per projection
+    K = log(1-C)/log(1-1/(N_pre N_post)) drawn with numpy (seeded) and handed to the reference's
+    `Synapses.connect(i=..., j=...)` (synapses.py:1704-1710), normally distributed weights
+    (87.8 pA +- 10 %, inhibition x -4, L4E->L23E doubled) and delays (1.5 +- 0.75 ms exc,
+    0.8 +- 0.4 ms inh).  ``scale`` shrinks the population sizes (in-degrees are preserved by
+    scaling K with it, as in the published down-scaling recipe without weight compensation).
+    ``poisson=False`` replaces the 8 Hz Poisson background by its mean current, which makes the
+    run deterministic (spike-exact comparison over short horizons); ``poisson=True`` uses
+    PoissonInput (binomial sampler on the device's Philox streams: statistical comparison)."""
+    b.seed(seed)
+    ms, mV, pA, pF, Hz = b.ms, b.mV, b.pA, b.pF, b.Hz
+    rng = np.random.RandomState(seed)
+    sizes = [max(1, int(round(n * scale))) for n in PD_SIZES]
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(starts[-1])
+    tau_m, tau_ref, tau_syn = 10 * ms, 2 * ms, 0.5 * ms
+    C_m, v_r, v_th = 250 * pF, -65 * mV, -50 * mV
+    w_ex, g, bg_rate = 87.8 * pA, 4.0, 8 * Hz
+    ns = dict(tau_m=tau_m, tau_syn=tau_syn, C_m=C_m, v_r=v_r, v_th=v_th)
+    eqs = """dv/dt = (v_r - v)/tau_m + (I + Iext)/C_m : volt (unless refractory)
+             dI/dt = -I/tau_syn : amp
+             Iext : amp (constant)"""
+    G = b.NeuronGroup(N, eqs, threshold="v > v_th", reset="v = v_r", refractory=tau_ref,
+                      method="exact", namespace=ns, name="pd_net")
+    G.v = (-58.0 + 10.0 * rng.randn(N)) * mV
+    kext = np.repeat(PD_KEXT, sizes).astype(float)
+    if not poisson:   # mean of the Poisson background: K_ext * rate * w * tau_syn
+        G.Iext = kext * float(bg_rate) * float(w_ex) * float(tau_syn) * b.amp
+    pre_all, post_all, w_all, d_all = [], [], [], []
+    for t in range(8):
+        for s_ in range(8):
+            c = PD_CONN[t][s_]
+            if c == 0.0:
+                continue
+            n_pre_full, n_post_full = PD_SIZES[s_], PD_SIZES[t]
+            k_full = np.log(1.0 - c) / np.log(1.0 - 1.0 / (n_pre_full * n_post_full))
+            k = int(round(k_full * scale))       # in-degree preserved: K/N_post constant
+            if k == 0:
+                continue
+            pre = rng.randint(0, sizes[s_], size=k) + starts[s_]
+            post = rng.randint(0, sizes[t], size=k) + starts[t]
+            exc = s_ % 2 == 0
+            w_mean = float(w_ex) * (2.0 if (s_ == 2 and t == 0) else 1.0) * (1.0 if exc else -g)
+            w = w_mean + 0.1 * abs(w_mean) * rng.randn(k)
+            w = np.maximum(w, 0.0) if exc else np.minimum(w, 0.0)
+            d = (1.5e-3 + 0.75e-3 * rng.randn(k)) if exc else (0.8e-3 + 0.4e-3 * rng.randn(k))
+            d = np.maximum(np.round(d / 1e-4), 1.0) * 1e-4      # whole steps, >= dt
+            pre_all.append(pre); post_all.append(post); w_all.append(w); d_all.append(d)  # noqa: E702
+    pre = np.concatenate(pre_all); post = np.concatenate(post_all)  # noqa: E702
+    order = np.lexsort((post, pre))              # (pre, post) order like a single connect() call
+    S = b.Synapses(G, G, "w : amp", on_pre="I_post += w", name="pd_syn")
+    S.connect(i=pre[order].astype(np.int32), j=post[order].astype(np.int32))
+    S.w = np.concatenate(w_all)[order] * b.amp
+    S.delay = np.concatenate(d_all)[order] * b.second
+    objs = dict(G=G, S=S)
+    if poisson:
+        for p_ in range(8):
+            sub = G[int(starts[p_]):int(starts[p_ + 1])]
+            objs[f"bg{p_}"] = b.PoissonInput(sub, "I", N=PD_KEXT[p_], rate=bg_rate, weight=w_ex)
+    if monitor:
+        objs["spikes"] = b.SpikeMonitor(G, name="pd_net_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("G", "I")]
+    return objs
+
+
 MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=synapses_only,
               spikegen=spikegen, gapjunction=gapjunction, timedarray=timedarray,
-              poisson_drive=poisson_drive, ragged=ragged)
+              poisson_drive=poisson_drive, ragged=ragged, potjans=potjans)
 
 
 def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):

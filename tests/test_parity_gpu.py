@@ -45,6 +45,9 @@ def _check(case, res, exact_state):
     ("cobahh_1000", False),
     # per-synapse weights are accumulated with fp64 atomics (order not deterministic)
     ("stdp_1000", False),
+    # Potjans-Diesmann microcircuit (8 populations, per-synapse weights and delays, 3 M synapses):
+    # currents are accumulated with fp64 atomics (order not deterministic)
+    ("potjans_small", False),
     # next rows of SURVEY.md 8(a10/f): SpikeGeneratorGroup (+ StateMonitor of synapses), summed
     # variables (gathered in the reference's summation order), TimedArray
     ("spikegen", True),
