@@ -605,6 +605,11 @@ class B200Device(CPPStandaloneDevice):
             if not self.is_device_codeobj(codeobj):
                 continue
             code = None
+            if self._b200_info[codeobj.name]["template"] == "synapses_push_spikes":
+                # no device code at all (the spike ring makes the push a no-op): its variables
+                # -- the per-synapse `delay` array above all -- are read by the HOST-side
+                # before_run block that builds the CSR, straight from the host arrays
+                continue
             for var in codeobj.variables.values():
                 if isinstance(var, ArrayVariable):
                     if (var.constant and var.read_only and var in self.dynamic_arrays
