@@ -77,6 +77,19 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(workload, timesteps_per_launch):
+    """DRAM bytes (read + write) of one launch of the persistent kernel, from this round's
+    `ncu --set full` capture of the same workload (profiles/ncu_traffic.json: bytes per
+    timestep of the captured launch x the timesteps of a bench launch); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            per_step = json.load(f)[workload]["dram_bytes_per_timestep"]
+    except (OSError, KeyError, ValueError):
+        return None
+    return per_step * timesteps_per_launch
+
+
 class ClockSampler:
     """SM clock / throttle-reason samples (NVML, every ~2 ms) kept only when they fall inside
     the timed step loops (`windows` = [(t0, t1)] in host epoch seconds)."""
@@ -254,6 +267,8 @@ def run_b200(args, rank, world):
     dev_s = sum(cnt(f"run{r}.device_seconds") for r in timed)
     e2e_s = sum(cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds") + cnt(f"run{r}.download_seconds")
                 for r in timed)
+    e2e_parts = {k: 1e3 * sum(cnt(f"run{r}.{k}_seconds") for r in timed) / max(len(timed), 1)
+                 for k in ("upload", "wall", "download")}
     events = sum(cnt(f"run{r}.events") for r in timed)
     steps = sum(cnt(f"run{r}.steps") for r in timed)
     persistent = all(cnt(f"run{r}.persistent") == 1 for r in timed)
@@ -272,7 +287,7 @@ def run_b200(args, rank, world):
     return dict(dev_s=dev_s, e2e_s=e2e_s, events=events, timesteps=steps, persistent=persistent,
                 h2d=cnt("h2d_bytes") / n_runs, d2h=cnt("d2h_bytes") / n_runs, launches=cnt("launches"),
                 clocks=clocks, n_neurons=n_neurons, n_syn=n_syn, build_seconds=build_seconds,
-                sim_steps=sim_steps, bytes_neuron=bytes_neuron, bytes_event=bytes_event,
+                sim_steps=sim_steps, bytes_neuron=bytes_neuron, bytes_event=bytes_event, e2e_parts=e2e_parts,
                 spikes=len(objs["spikes"].i[:]) if "spikes" in objs else None)
 
 
@@ -426,10 +441,14 @@ def main():
         "us_per_timestep": 1e6 * dev_s / max(timesteps, 1),
         "clocks": r["clocks"],
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": r["h2d"],
-                "d2h_bytes_per_step": r["d2h"]},
+                "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": {"upload": r["e2e_parts"]["upload"], "loop_host_clock": r["e2e_parts"]["wall"],
+                                "download": r["e2e_parts"]["download"]}},
         "gpu_launches": int(r["launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": _ncu_traffic(args.workload, r["sim_steps"]),
+                     "algorithmic_bytes_per_launch": algo_bytes / max(args.steps, 1),
+                     "peak_source": peak_src,
                      "kernel": "persistent step kernel (stateupdate+threshold+propagation+monitors)",
                      "algorithmic_bytes": f"{bytes_neuron} B/neuron-step + {bytes_event} B/event"},
     }
