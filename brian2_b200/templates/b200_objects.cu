@@ -64,6 +64,8 @@ void _b200_sync_constants();                 // defined next to the kernels (own
 int _b200_grid_size();                       // CTAs of every kernel of this project (co-resident)
 _B200Clocks _b200_clocks_now();
 void _b200_prepare_steps(long long steps, bool exact);   // make monitor buffers large enough
+void _b200_prefault_start(long long steps);   // host-side: map the pages the next records will land in
+void _b200_prefault_join();
 void _b200_launch_begin(const char* name);
 void _b200_launch_end(const char* name);
 unsigned long long _b200_events_delivered();
@@ -78,6 +80,7 @@ int _b200_array_copy_in(const char* name, const void* data, size_t nbytes);
 
 {% macro cpp_file() %}
 #include "b200_objects.h"
+#include <thread>
 #include "brianlib/clocks.h"
 #include <chrono>
 #include <map>
@@ -125,6 +128,7 @@ _B200Clocks _b200_clocks_now()
 
 void _b200_upload()
 {
+    _b200_prefault_join();
     using namespace brian;
     b200::runtime_init();
     b200::RuntimeState& st = b200::state();
@@ -273,10 +277,53 @@ void _b200_prepare_steps(long long steps, bool exact)
     if (changed) _b200_sync_constants();
 }
 
+// While the persistent kernel runs the host has nothing to do: a helper thread reserves the
+// capacity the monitors' host vectors will need after the launch (event rate seen so far x1.5)
+// and touches those pages, so that the download at the end of run() copies into mapped memory
+// instead of paying a first-touch page fault per 4 KB (that was 3/4 of the end-to-end overhead of
+// a COBAHH run).  Nothing else touches these vectors between _b200_prefault_start and
+// _b200_prefault_join (called by _b200_download / _b200_upload).
+static struct _B200PrefaultThread : std::thread {
+    using std::thread::operator=;
+    ~_B200PrefaultThread() { if (joinable()) join(); }   // never leave a joinable thread behind
+} _b200_prefault_thread;
+template <typename T>
+static void _b200_prefault_vector(std::vector<T>& v, size_t need)
+{
+    if (v.capacity() < need) v.reserve(std::max(need, 2 * v.capacity()));
+    volatile char* p = (volatile char*)v.data();
+    const size_t from = (v.size() * sizeof(T)) & ~(size_t)4095, to = v.capacity() * sizeof(T);
+    for (size_t off = from + 4096; off < to; off += 4096) p[off] = 0;
+}
+void _b200_prefault_join()
+{
+    if (_b200_prefault_thread.joinable()) _b200_prefault_thread.join();
+}
+void _b200_prefault_start(long long steps)
+{
+    _b200_prefault_join();
+    {% for mon in b200_monitors %}
+    {% if mon.kind == 'spike' %}
+    const size_t _need_{{mon.name}} = (size_t)(_monN_ub_{{mon.name}} + (_b200_steps_prepared > steps
+        ? (long long)(1.5 * (double)_monN_ub_{{mon.name}} / (double)(_b200_steps_prepared - steps) * (double)steps) : 0));
+    {% else %}
+    const size_t _need_{{mon.name}} = (size_t)(_monN_ub_{{mon.name}} + steps);
+    {% endif %}
+    {% endfor %}
+    _b200_prefault_thread = std::thread([=]() {
+        {% for a in b200_arrays %}
+        {% if a.used and a.kind == 'dynamic1d' and a.monitor %}
+        _b200_prefault_vector(brian::{{a.dyn_name}}, _need_{{a.monitor}});
+        {% endif %}
+        {% endfor %}
+    });
+}
+
 void _b200_download()
 {
     using namespace brian;
     b200::RuntimeState& st = b200::state();
+    _b200_prefault_join();
     const auto _t0 = std::chrono::high_resolution_clock::now();
     B200_CUDA(cudaDeviceSynchronize());
     {% for mon in b200_monitors %}

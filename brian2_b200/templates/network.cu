@@ -74,6 +74,7 @@ void Network::run(const double duration, void (*report_func)(const double, const
         (*i)->set_interval(t, t_end);
 
     // host mirrors -> device (not part of the timed loop, like the reference's _load_arrays)
+    const double _upload_before = b200::state().upload_seconds;
     _b200_upload();
 
     // device-side clock of the loop: CUDA events on the launching stream
@@ -81,7 +82,6 @@ void Network::run(const double duration, void (*report_func)(const double, const
     if (!_ev_start) { B200_CUDA(cudaEventCreate(&_ev_start)); B200_CUDA(cudaEventCreate(&_ev_stop)); }
     const unsigned long long _events_before = _b200_events_delivered();
     const long long _steps_before = Network::_b200_steps_run;
-    const double _upload_before = b200::state().upload_seconds;
     B200_CUDA(cudaDeviceSynchronize());
     // several GPUs: the ranks enter the loop together (their uploads take different times, and a
     // rank whose peer starts late would spin on the peer's first spike list inside the timed loop)
@@ -118,6 +118,7 @@ void Network::run(const double duration, void (*report_func)(const double, const
             t = clock->t[0];
             const long long want = std::min<long long>(chunk, clock->steps_left());
             _b200_prepare_steps(want, true);
+            _b200_prefault_start(want);
             const hrc::time_point c0 = hrc::now();
             const long long done = plan->run_chunk(want);
             clock->advance(done);
