@@ -116,3 +116,106 @@ def test_product_never_touches_the_oracle():
             if "hotpath_oracle" in text or re.search(r"\bimport\s+oracle\b|from\s+oracle\b", text):
                 offenders.append(fn)
     assert not offenders, offenders
+
+
+def test_host_only_arrays_are_not_uploaded(cuba_project):
+    """`_synaptic_pre/_post` and the per-synapse `delay` are read by the host-side CSR build only
+    (the CUDA templates take both ends of a synapse from the CSR): no upload of them is generated,
+    while every state array of the neurons still is."""
+    src = open(os.path.join(cuba_project, "b200_objects.cpp")).read()
+    uploads = re.findall(r"b200::upload_(?:vector|array|records)\(_A_host\.(\w+)", src)
+    assert "_array_cuba_P_v" in uploads and "_array_cuba_P_ge" in uploads
+    assert not [u for u in uploads if "_synaptic_p" in u or u.endswith("_delay")], uploads
+
+
+def _emulate_propagation(bn, blr, rows_len, nwarps, mode):
+    """Python restatement of the work distribution of templates/synapses.cu for one group of
+    delay bins: bn[b] rows (spikes) in bin b, every row padded to blr[b] lines of 32 slots,
+    rows_len[b][s] real lengths.  Returns a {(bin, row, slot): visits} counter."""
+    from collections import Counter
+
+    visits = Counter()
+    nb = len(bn)
+    bexcl = np.concatenate([[0], np.cumsum([bn[b] * blr[b] for b in range(nb)])])
+    rexcl = np.concatenate([[0], np.cumsum(bn)])
+    nlines, nrows = int(bexcl[-1]), int(rexcl[-1])
+
+    def line_share(a, b):           # the `while (_a < _b)` loop: lines [a, b) of the sequence
+        while a < b:
+            L = int(np.searchsorted(bexcl, a, side="right") - 1)
+            L = min(L, nb - 1)
+            while bn[L] * blr[L] == 0:      # the ballot picks the last bin whose offset <= a
+                L += 1
+            loc = a - int(bexcl[L])
+            s, l0 = divmod(loc, blr[L])
+            nl = min(blr[L] - l0, b - a)
+            a += nl
+            n = rows_len[L][s]
+            rbeg = 0                # (alignment of the row start does not change the coverage)
+            lo, hi = rbeg + 32 * l0, min(n, rbeg + 32 * (l0 + nl))
+            for k in range(lo, hi):
+                visits[(L, s, k)] += 1
+
+    if mode == "row":
+        assert nrows <= nwarps
+        k = nwarps // nrows
+        for w in range(nwarps):
+            r, part = divmod(w, k)
+            if r >= nrows:
+                continue
+            L = int(np.searchsorted(rexcl, r, side="right") - 1)
+            s = r - int(rexcl[L])
+            per = -(-blr[L] // k)
+            lo = min(blr[L], part * per)
+            hi = min(blr[L], lo + per)
+            a = int(bexcl[L]) + s * blr[L] + lo
+            line_share(a, a + hi - lo)
+    elif mode == "line":
+        for w in range(nwarps):
+            line_share(w * nlines // nwarps, (w + 1) * nlines // nwarps)
+    elif mode == "ticket":
+        t = 0
+        while 32 * t < nlines:      # whoever draws ticket t handles lines [32 t, 32 t + 32)
+            line_share(32 * t, min(32 * t + 32, nlines))
+            t += 1
+    elif mode == "gather":
+        for w in range(nwarps):
+            ra, rb = w * nrows // nwarps, (w + 1) * nrows // nwarps
+            for r0 in range(ra, rb, 32):
+                batch = []
+                for r in range(r0, min(r0 + 32, rb)):
+                    L = int(np.searchsorted(rexcl, r, side="right") - 1)
+                    batch.append((L, r - int(rexcl[L])))
+                lens = [rows_len[L][s] for L, s in batch]
+                lexcl = np.concatenate([[0], np.cumsum(lens)])
+                for slot in range(int(lexcl[-1])):
+                    j = int(np.searchsorted(lexcl, slot, side="right") - 1)
+                    L, s = batch[j]
+                    visits[(L, s, slot - int(lexcl[j]))] += 1
+    return visits
+
+
+@pytest.mark.parametrize("mode", ["row", "line", "ticket", "gather"])
+def test_propagation_work_distribution_covers_every_synapse_once(mode):
+    """Every (delay bin, spiking row, synapse slot) is delivered exactly once, for ragged rows,
+    empty bins and empty rows, in each of the four ways templates/synapses.cu deals the work
+    out (the arithmetic is restated in `_emulate_propagation`)."""
+    rng = np.random.RandomState({"row": 1, "line": 2, "ticket": 3, "gather": 4}[mode])
+    for trial in range(20):
+        nb = int(rng.randint(1, 7))
+        nwarps = int(rng.choice([16, 48, 160]))
+        maxlen = [int(rng.randint(0, 130 if mode != "gather" else 66)) for _ in range(nb)]
+        blr = [max(1, (m + 62) >> 5) for m in maxlen]
+        if mode == "row":
+            bn = [int(rng.randint(0, max(1, nwarps // nb))) for _ in range(nb)]
+        elif mode == "gather":
+            bn = [int(rng.randint(0, 3 * nwarps)) for _ in range(nb)]
+        else:
+            bn = [int(rng.randint(0, 40)) for _ in range(nb)]
+        if sum(bn) == 0:
+            bn[0] = 1
+        rows_len = [[int(rng.randint(0, m + 1)) for _ in range(n)] for n, m in zip(bn, maxlen)]
+        visits = _emulate_propagation(bn, blr, rows_len, nwarps, mode)
+        expected = {(b, s, k) for b in range(nb) for s in range(bn[b]) for k in range(rows_len[b][s])}
+        assert set(visits) == expected, (mode, trial)
+        assert all(v == 1 for v in visits.values()), (mode, trial)
