@@ -88,6 +88,24 @@ def test_in_loop_random_numbers_statistics(brian, project_dir):
     np.testing.assert_allclose(res["G_v"].mean(), gold["G_v"].mean(), rtol=0.1)
 
 
+def test_float32_mode(brian, project_dir):
+    """`prefs.core.default_float_dtype = float32` (`-DB200_FLOAT32`): CUBA-1000 in single precision.
+    A recurrent network amplifies rounding differences, so the comparison with the fp64 golden run
+    is the reference's own cross-precision criterion (tests/test_cpp_standalone.py:41-44 style):
+    total spike count within 3 %, population mean of `v` within 1 mV, state arrays are float32."""
+    model, kwds = CASES["cuba_1000"]
+    try:
+        objs, res = models.run_model(brian, model, "b200", project_dir,
+                                     prefs_update={"core.default_float_dtype": np.float32}, **kwds)
+    finally:
+        brian.prefs["core.default_float_dtype"] = np.float64
+    gold = np.load(os.path.join(GOLDEN, "cuba_1000.npz"))
+    assert res["P_v"].dtype == np.float32
+    n_gold, n_f32 = len(gold["spikes_i"]), len(res["spikes_i"])
+    assert abs(n_f32 - n_gold) <= 0.03 * n_gold, (n_f32, n_gold)
+    assert abs(float(res["P_v"].mean()) - float(gold["P_v"].mean())) < 1e-3
+
+
 def test_device_math_identical(tmp_path):
     """The constant-bank exp/expm1/exprel of csrc/b200_functions.cuh return the same bits as CUDA's
     library functions (with which the parity tolerances above were established) for 4 x 2^24
