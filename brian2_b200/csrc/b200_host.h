@@ -245,6 +245,14 @@ struct EventSpace {
         const int need = required_slots();
         if (ids && slots >= need && N == N_ && nb == nb_) return;
         const int new_nseg = st.world * nb_;
+        {   // the thresholder keeps one bit per owned element of a lane in a 64-bit mask
+            int64_t lo, hi;
+            rank_range_host(N_, st.rank, st.world, lo, hi);
+            const int64_t tasks = (hi - lo + 31) >> 5, warps = (int64_t)nb_ * kWarps;
+            if ((tasks + warps - 1) / warps > kMaxOwnedIters)
+                throw std::runtime_error("b200: group too large for one GPU (more than 64 x 32 elements per "
+                                         "warp of the grid); partition the network over more GPUs");
+        }
         const bool keep = ids && N == N_ && nb == nb_;
         close_peers();
         ids = realloc_ring(ids, slots, (size_t)N, need, (size_t)N_, timestep, keep);
