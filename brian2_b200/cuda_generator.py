@@ -360,6 +360,19 @@ class CUDACodeGenerator(CPPCodeGenerator):
                 m = re.match(r"^const int32_t (_presynaptic_idx|_postsynaptic_idx) = \w+\[_idx\];$", line)
                 if m:
                     lines[n] = f"const int32_t {m.group(1)} = {ends[m.group(1)]};"
+        # Pure scatter with per-synapse operands (`x_post += w`): the loads of the synaptic variables
+        # (index `_idx`, never written here) move into the template's preload stage as well, next
+        # to the index stream, so that no reduction waits for its own weight load.
+        self._b200_preloads = []
+        if self._b200_unroll > 1:
+            kept = []
+            for line in lines:
+                m = re.match(r"^const (\w+) (\w+) = (\w+)\[_idx\];$", line)
+                if m and m.group(2) in load_read and idx_of.get(m.group(2)) == "_idx" and m.group(2) not in write:
+                    self._b200_preloads.append((m.group(1), m.group(2), m.group(3)))
+                else:
+                    kept.append(line)
+            lines = kept
         lines += self.translate_to_declarations(load_read | inplace_targets, write, indices)
         tmp_count = 0
         for stmt in statements:
@@ -480,6 +493,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
         kwds["b200_serial"] = serial
         kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)
         kwds["b200_gather_unroll"] = 2 if kwds["b200_unroll"] > 1 else 1
+        kwds["b200_preloads"] = [] if serial else list(getattr(self, "_b200_preloads", []))
         # remembered by the device for the barrier analysis of the persistent kernel
         access["serial"] = serial
         self.device._b200_access[self.name] = access

@@ -172,6 +172,9 @@
                 for (int _base = 0; _base < _nslots; _base += 32 * {{b200_gather_unroll}})
                 {
                     int _b200_tg[{{b200_gather_unroll}}], _b200_sy[{{b200_gather_unroll}}], _b200_sa[{{b200_gather_unroll}}];
+                    {% for ctype, var, ptr in b200_preloads %}
+                    {{ctype}} _b200_rd_{{var}}[{{b200_gather_unroll}}];
+                    {% endfor %}
                     #pragma unroll
                     for (int _u = 0; _u < {{b200_gather_unroll}}; ++_u)
                     {
@@ -189,6 +192,9 @@
                         _b200_sa[_u] = __shfl_sync(0xffffffffu, _srcabs, _jlo);
                         _b200_tg[_u] = _sv ? __ldg(_pw.csr_target + _k) : -1;
                         _b200_sy[_u] = (_sv && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
+                        {% for ctype, var, ptr in b200_preloads %}
+                        _b200_rd_{{var}}[_u] = _sv ? {{ptr}}[_b200_sy[_u]] : ({{ctype}})0;
+                        {% endfor %}
                     }
                     #pragma unroll
                     for (int _u = 0; _u < {{b200_gather_unroll}}; ++_u)
@@ -198,6 +204,9 @@
                         const int _b200_tgt_idx = _b200_tg[_u];
                         const int _b200_src_idx = _b200_sa[_u];
                         const int _vectorisation_idx = _idx;
+                        {% for ctype, var, ptr in b200_preloads %}
+                        const {{ctype}} {{var}} = _b200_rd_{{var}}[_u];
+                        {% endfor %}
                         {% if b200_uses_rng %}
                         b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
                         {% endif %}
@@ -272,12 +281,18 @@
             for (int _kb = _k0; _kb < _end; _kb += 32 * {{b200_unroll}})
             {
                 int _b200_tg[{{b200_unroll}}], _b200_sy[{{b200_unroll}}];
+                {% for ctype, var, ptr in b200_preloads %}
+                {{ctype}} _b200_rd_{{var}}[{{b200_unroll}}];
+                {% endfor %}
                 #pragma unroll
                 for (int _u = 0; _u < {{b200_unroll}}; ++_u)
                 {
                     const int _k = _kb + 32 * _u;
                     _b200_tg[_u] = _k < _end ? __ldg(_pw.csr_target + _k) : 0;
                     _b200_sy[_u] = (_k < _end && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
+                    {% for ctype, var, ptr in b200_preloads %}
+                    _b200_rd_{{var}}[_u] = _k < _end ? {{ptr}}[_b200_sy[_u]] : ({{ctype}})0;
+                    {% endfor %}
                 }
                 #pragma unroll
                 for (int _u = 0; _u < {{b200_unroll}}; ++_u)
@@ -286,6 +301,9 @@
                     const int _idx = _b200_sy[_u];
                     const int _b200_tgt_idx = _b200_tg[_u];
                     const int _vectorisation_idx = _idx;
+                    {% for ctype, var, ptr in b200_preloads %}
+                    const {{ctype}} {{var}} = _b200_rd_{{var}}[_u];
+                    {% endfor %}
                     {% if b200_uses_rng %}
                     b200::Rng _rng = b200::rng_init(_A._seed, {{b200_stream_id}}u, _idx, _b200_timestep);
                     {% endif %}
