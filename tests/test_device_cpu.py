@@ -219,3 +219,31 @@ def test_propagation_work_distribution_covers_every_synapse_once(mode):
         expected = {(b, s, k) for b in range(nb) for s in range(bn[b]) for k in range(rows_len[b][s])}
         assert set(visits) == expected, (mode, trial)
         assert all(v == 1 for v in visits.values()), (mode, trial)
+
+
+@pytest.fixture(scope="module")
+def ragged_project(brian):
+    import __graft_entry__ as ge
+
+    directory, objs = ge.build_project("ragged", directory=os.path.join(ge.PREBUILT, "cpu_ragged"))
+    return directory
+
+
+def test_generated_propagation_code_of_ragged_case(ragged_project):
+    """Generator decisions for the two pathways of the `ragged` model (cross-compiled for sm_100a by
+    the fixture): `x_post += w` is a pure scatter -- unrolled delivery, `w` preloaded with the
+    index stream, both ends of the synapse taken from the CSR; the on_post code writes synaptic
+    and presynaptic variables -- no unrolling, no preload, plain store to `w`."""
+    pre = open(os.path.join(ragged_project, "code_objects", "rg_S_pre_codeobject.cuh")).read()
+    post = open(os.path.join(ragged_project, "code_objects", "rg_S_post_codeobject.cuh")).read()
+    assert "double _b200_rd_w[4];" in pre and "const double w = _b200_rd_w[_u];" in pre
+    assert "const int32_t _postsynaptic_idx = _b200_tgt_idx;" in pre
+    assert "b200::atomic_add(&_ptr_array_rg_neurons_x[_postsynaptic_idx]" in pre
+    assert "_synaptic_post[_idx]" not in pre.split("_dev_rg_S_pre_codeobject")[1]
+    assert "_b200_rd_" not in post
+    assert "const int32_t _presynaptic_idx = _b200_tgt_idx;" in post     # on_post: the other end is pre
+    assert "b200::atomic_add(&_ptr_array_rg_neurons_y[_presynaptic_idx]" in post
+    assert "_ptr_array_rg_S_w[_idx] = w;" in post
+    # three grid barriers: spikes -> on_pre -> on_post (reads what on_pre wrote) -> end of step
+    src = open(os.path.join(ragged_project, "b200_kernels.cu")).read()
+    assert "grid barriers per step: 3" in src
