@@ -161,6 +161,7 @@ class B200Device(CPPStandaloneDevice):
         self._b200_info = {}
         #: one entry per `Network.run` call: list of (clock, codeobj)
         self._b200_plans = []
+        self._b200_memo_slots = {}      # state monitor name -> per-CTA memo slot (statemonitor.cu)
         self._b200_stream_counter = 0
         self._b200_seed = None
         self._b200_library = None
@@ -230,9 +231,10 @@ class B200Device(CPPStandaloneDevice):
                 src = owner.source
                 template_kwds["b200_source_size"] = int(len(src)) if isinstance(src, NeuronGroup) else None
                 # slot of the per-CTA "records nothing here" memo (csrc/b200_runtime.cuh)
-                self._b200_memo_slots = getattr(self, "_b200_memo_slots", {})
-                slot = self._b200_memo_slots.setdefault(owner.name, len(self._b200_memo_slots) % 8)
-                template_kwds["b200_memo_slot"] = slot
+                if owner.name not in self._b200_memo_slots:
+                    n = len(self._b200_memo_slots)
+                    self._b200_memo_slots[owner.name] = n if n < 8 else None   # 8 memo slots per CTA
+                template_kwds["b200_memo_slot"] = self._b200_memo_slots[owner.name]
         # seen by the CUDA generator while it translates this code object (pathway direction)
         self._b200_current_template_kwds = template_kwds
         codeobj = super().code_object(

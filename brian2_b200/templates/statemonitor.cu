@@ -12,6 +12,7 @@
     // Does this CTA own any recorded element?  Decided once per launch (the recorded indices do
     // not change inside a run); CTAs that own none leave at once in every later step.
     const b200::Slice _mine = b200::owned_cta((int64_t){{b200_source_size}}, _ctx);
+    {% if b200_memo_slot is not none %}
     int* _memo = b200::monitor_memo() + {{b200_memo_slot}};
     if (*_memo < 0)
     {
@@ -26,6 +27,7 @@
         __syncthreads();
     }
     if (*_memo == 1 && _ctx.bid != 0) return;
+    {% endif %}
     {% endif %}
     const int _par = (int)(_clks.{{b200_clock}}.timestep & 1);
     long long* _monN = _A._monN_{{owner.name}};
