@@ -43,6 +43,7 @@ CASES = {
                                                    hetero_bins=5)),
     # Potjans-Diesmann microcircuit at 1 % of the neurons (in-degrees preserved), DC background
     "potjans_small": ("potjans", dict(scale=0.01, duration=0.05)),
+    "submon": ("submon", dict(N=600, duration=0.05)),
     "ragged": ("ragged", dict(N=600, duration=0.03)),
     "spikegen": ("spikegen", dict(N=200, n_spikes=3000, duration=0.05)),
     "spikegen_period": ("spikegen", dict(N=200, n_spikes=600, duration=0.05, period_ms=10.0)),

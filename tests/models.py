@@ -418,7 +418,38 @@ MODELS = dict(cuba=cuba, cobahh=cobahh, brunel=brunel, stdp=stdp, synapses_only=
               poisson_drive=poisson_drive, ragged=ragged, potjans=potjans)
 
 
-def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, **model_kwds):
+def submon(b, N=600, duration=0.05, seed=77):
+    """Monitors of SUBGROUPS (spikemonitor.cpp:15-33 restricts the spike list to
+    [_source_start, _source_stop); ratemonitor.cpp likewise; statemonitor of a subgroup) on a small
+    CUBA-like network, plus a pathway whose source and target are subgroups."""
+    b.seed(seed)
+    ms, mV = b.ms, b.mV
+    eqs = """dv/dt = (ge+gi-(v+49*mV))/(20*ms) : volt (unless refractory)
+             dge/dt = -ge/(5*ms) : volt
+             dgi/dt = -gi/(10*ms) : volt"""
+    P = b.NeuronGroup(N, eqs, threshold="v>-50*mV", reset="v=-60*mV", refractory=5 * ms, method="exact",
+                      name="sm_P")
+    P.v = "-60*mV + rand()*10*mV"
+    Ce = b.Synapses(P[: N * 4 // 5], P, on_pre="ge += 1.62*mV", name="sm_Ce")
+    Ci = b.Synapses(P[N * 4 // 5:], P[N // 10:], on_pre="gi -= 9*mV", name="sm_Ci")
+    Ce.connect(p=0.1)
+    Ci.connect(p=0.1)
+    objs = dict(P=P, Ce=Ce, Ci=Ci)
+    objs["spikes"] = b.SpikeMonitor(P, name="sm_all")
+    objs["sub_spikes"] = b.SpikeMonitor(P[N // 6: N // 2], name="sm_sub")
+    objs["tail_spikes"] = b.SpikeMonitor(P[N - 50:], name="sm_tail")
+    objs["sub_rate"] = b.PopulationRateMonitor(P[N // 3: 2 * N // 3], name="sm_rate")
+    objs["sub_trace"] = b.StateMonitor(P[N // 2:], "v", record=[0, 5, 17], name="sm_trace")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("P", "v"), ("P", "ge"), ("P", "gi")]
+    return objs
+
+
+MODELS["submon"] = submon
+
+
+def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, n_runs=1, **model_kwds):
     """Build + run ``name`` on ``device_name``; returns (objs, results dict of numpy arrays).
 
     All objects carry explicit names: Brian orders code objects of the same schedule slot by
@@ -439,7 +470,8 @@ def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=Non
     b.defaultclock.dt = 0.1 * b.ms
     objs = MODELS[name](b, **model_kwds)
     net = objs["net"]
-    net.run(objs["duration"] * b.second, namespace={})
+    for _ in range(n_runs):     # several run() calls of equal length (same total duration)
+        net.run(objs["duration"] / n_runs * b.second, namespace={})
     b.device.build(directory=directory, compile=True, run=True, with_output=False, **(build_kwds or {}))
     res = collect_results(b, objs)
     return objs, res

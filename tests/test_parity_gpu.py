@@ -150,3 +150,21 @@ def test_multi_gpu_sharded_parity():
            "synapses_only_short", "synapses_only_heavy"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     assert "MULTIGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_monitors_of_subgroups(brian, project_dir):
+    """SpikeMonitor / PopulationRateMonitor / StateMonitor of subgroups and pathways between
+    subgroups (spikemonitor.cpp:15-33, ratemonitor.cpp:6-36; absolute indices with offsets):
+    bit-identical with the reference."""
+    model, kwds = CASES["submon"]
+    objs, res = models.run_model(brian, model, "b200", project_dir, **kwds)
+    _check("submon", res, True)
+
+
+def test_two_run_calls_equal_one(brian, project_dir):
+    """`run(50 ms); run(50 ms)` leaves exactly the records and state of the reference's single
+    `run(100 ms)`: the device state, the spike ring and the monitor records (transferred
+    incrementally, b200_host.h: upload_records / download_records) carry over between runs."""
+    model, kwds = CASES["cuba_1000"]
+    objs, res = models.run_model(brian, model, "b200", project_dir, n_runs=2, **kwds)
+    _check("cuba_1000", res, True)
