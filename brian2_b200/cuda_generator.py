@@ -436,6 +436,14 @@ class CUDACodeGenerator(CPPCodeGenerator):
                     keep_exp_pow=bool(prefs["devices.b200.fuse_exp_pow"]),
                 ).run(ve_block)
             sc_read, sc_write, sc_indices, sc_cond = self.arrays_helper(sc_block)
+            if sc_write:
+                # (stateupdate.cpp is ALLOWS_SCALAR_WRITE: e.g. `run_regularly('shared_var = ...')`.
+                # On the device every thread evaluates the scalar block, so a shared variable
+                # that is read and written there would need two grid barriers per step.)
+                raise NotImplementedError(
+                    "b200 device: code that writes to shared (scalar) variables inside the simulation "
+                    f"loop ({', '.join(sorted(sc_write))} in '{self.name}')"
+                )
             ve_read, ve_write, ve_indices, ve_cond = self.arrays_helper(ve_block)
             # scalar variables needed by the vector code are read once, in the scalar block
             for varname in set(ve_read):

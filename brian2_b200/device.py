@@ -250,6 +250,10 @@ class B200Device(CPPStandaloneDevice):
             compiler_kwds=compiler_kwds,
         )
         if codeobj_class is B200CodeObject:
+            try:    # a strong reference: `build()` may be called after the script's objects went
+                owner = owner.__repr__.__self__     # out of scope (build_on_run=False)
+            except (AttributeError, ReferenceError):
+                pass
             self._b200_info[codeobj.name] = {
                 "template": template_name,
                 "owner": owner,

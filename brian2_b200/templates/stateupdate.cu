@@ -1,4 +1,5 @@
 {# USES_VARIABLES { N } #}
+{# ALLOWS_SCALAR_WRITE #}
 {# Per-element state update: brian2/devices/cpp_standalone/templates/stateupdate.cpp:5-22.
    One element per lane, warp-contiguous owned slices => 256 B coalesced fp64 requests. #}
 {% extends 'common_group.cu' %}
