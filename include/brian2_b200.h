@@ -78,8 +78,9 @@ int b200_set_option(const char* key, double value);
 
 /* Counters: "launches", "events" (delivered synaptic events), "steps", "h2d_bytes",
  * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "grid", "runs", and per
- * Network::run call "run<i>.device_seconds|wall_seconds|upload_seconds|download_seconds|events|
- * steps|persistent".  -1 if unknown. */
+ * Network::run call "run<i>.device_seconds|wall_seconds|t0_unix|upload_seconds|download_seconds|
+ * events|steps|persistent"; "phase<k*512+i>" = cycles sampled CTA k (first, 1/4, 3/4, last of the
+ * grid) spent in phase i of the persistent kernel (profile_phases builds).  -1 if unknown. */
 double b200_get_counter(const char* key);
 
 /* Per-code-object device seconds (profile mode).  Fills up to `cap` entries, returns the count.
