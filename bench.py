@@ -382,10 +382,14 @@ def main():
     hbm_peak, peak_src = _peaks()
     model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
     config = {
-        "workload": f"{args.workload}: {model} {kwds}, dt=0.1ms, fp64, SpikeMonitor(+3 v traces for COBAHH)",
+        "workload": f"{args.workload}: {model} {kwds}, dt=0.1ms, fp64, "
+                    + ("SpikeMonitor + StateMonitor of 3 voltage traces" if model == "cobahh" else
+                       "no monitors" if model == "synapses_only" else "SpikeMonitor(s)"),
         "connectivity": "reference Synapses.connect (host, mt19937), identical on both arms",
-        "l2": "working set (state + CSR) is comparable to the 126 MB L2 by nature of the workload; "
-              "every timed step starts after a fresh H2D upload of all arrays, no explicit flush",
+        "l2": "no explicit flush: a bench step is one run() of thousands of simulation timesteps over the "
+              "same state and CSR (a simulation re-reads its working set every timestep by nature; whether "
+              "it is L2 resident is a property of the workload: COBAHH-256k state 14 MB + CSR 82 MB vs "
+              "126 MB of L2); every timed step starts after the H2D upload of the state arrays",
     }
 
     if args.impl == "reference":
