@@ -66,6 +66,20 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
     return v;
 }
 
+// One word of the packed CSR index stream (immutable during a run: non-coherent load).  With
+// -DB200_CSR_EVICT_LAST (prefs.devices.b200.csr_l2_evict_last) the line is tagged evict_last in L2.
+__device__ __forceinline__ int ld_index(const int* p) {
+#ifdef B200_CSR_EVICT_LAST
+    unsigned long long pol;
+    int v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // system-scope flavours (multi-GPU: data and flags cross NVLink into peer memory)
 // ---------------------------------------------------------------------------------------------

@@ -136,6 +136,15 @@ prefs.register_preferences(
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
+    csr_l2_evict_last=BrianPreference(
+        default=False,
+        docs="""
+        EXPERIMENTAL (not measured yet): read the packed CSR index stream with an L2 `evict_last`
+        cache policy, so that the rows of neurons that fire rarely survive in the 126 MB L2 between
+        their spikes instead of being refetched from DRAM (COBAHH-256k: the last load of the
+        propagation chain).  A pure cache hint: results do not change.
+        """,
+    ),
 )
 
 
@@ -929,6 +938,8 @@ class B200Device(CPPStandaloneDevice):
         flags.append("-fmad=true" if prefs.devices.b200.fmad else "-fmad=false")
         if prefs.core.default_float_dtype == np.float32:
             flags.append("-DB200_FLOAT32")
+        if prefs.devices.b200.csr_l2_evict_last:
+            flags.append("-DB200_CSR_EVICT_LAST")
         return " ".join(flags)
 
     def generate_makefile(self, writer, compiler, compiler_flags, linker_flags, nb_threads, debug):

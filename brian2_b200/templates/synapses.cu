@@ -190,7 +190,7 @@
                         }
                         const int _k = __shfl_sync(0xffffffffu, _rbeg, _jlo) + _sl - __shfl_sync(0xffffffffu, _lexcl, _jlo);
                         _b200_sa[_u] = __shfl_sync(0xffffffffu, _srcabs, _jlo);
-                        _b200_tg[_u] = _sv ? __ldg(_pw.csr_target + _k) : -1;
+                        _b200_tg[_u] = _sv ? b200::ld_index(_pw.csr_target + _k) : -1;
                         _b200_sy[_u] = (_sv && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
                         {% for ctype, var, ptr in b200_preloads %}
                         _b200_rd_{{var}}[_u] = _sv ? {{ptr}}[_b200_sy[_u]] : ({{ctype}})0;
@@ -288,7 +288,7 @@
                 for (int _u = 0; _u < {{b200_unroll}}; ++_u)
                 {
                     const int _k = _kb + 32 * _u;
-                    _b200_tg[_u] = _k < _end ? __ldg(_pw.csr_target + _k) : 0;
+                    _b200_tg[_u] = _k < _end ? b200::ld_index(_pw.csr_target + _k) : 0;
                     _b200_sy[_u] = (_k < _end && !_pw.identity) ? __ldg(_pw.syn_ids + _k) : _k;
                     {% for ctype, var, ptr in b200_preloads %}
                     _b200_rd_{{var}}[_u] = _k < _end ? {{ptr}}[_b200_sy[_u]] : ({{ctype}})0;
