@@ -247,3 +247,35 @@ def test_generated_propagation_code_of_ragged_case(ragged_project):
     # three grid barriers: spikes -> on_pre -> on_post (reads what on_pre wrote) -> end of step
     src = open(os.path.join(ragged_project, "b200_kernels.cu")).read()
     assert "grid barriers per step: 3" in src
+
+
+def _schedule_of(case):
+    import __graft_entry__ as ge
+
+    directory, _ = ge.build_project(case, directory=os.path.join(ge.PREBUILT, "cpu_" + case))
+    src = open(os.path.join(directory, "b200_kernels.cu")).read()
+    return re.search(r"schedule: (.*)\n", src).group(1).strip(), src
+
+
+def test_barrier_plan_of_brunel(brian):
+    """`v += J` (exc) and `v += -g*J` (inh) scatter into the same array: the deliveries must not
+    interleave if `v` is to stay bit-identical with the reference (which delivers all of exc, then
+    all of inh), and the resetter's private write `v = V_r` must follow both: 4 barriers."""
+    sched, src = _schedule_of("brunel_hetero")
+    phases = [p.split() for p in sched.split("|")]
+    assert [len(p) for p in phases] == [2, 2, 1, 3], sched
+    assert phases[1][-1] == "brunel_exc_pre_codeobject" and phases[2] == ["brunel_inh_pre_codeobject"]
+    assert phases[3][0] == "brunel_neurons_spike_resetter_codeobject"
+    assert "grid barriers per step: 4" in src
+
+
+def test_barrier_plan_of_stdp(brian):
+    """on_pre (order -1) and on_post (order +1) of one Synapses object touch the same synaptic
+    variables (`w`, `Apre`, `Apost`, `lastupdate`): a barrier separates them; both thresholders
+    share the first phase with both state updaters (element-private chains)."""
+    sched, src = _schedule_of("stdp_1000")
+    phases = [p.split() for p in sched.split("|")]
+    assert len(phases) == 3, sched
+    assert "stdp_S_pre_codeobject" in phases[1] and phases[2][0] == "stdp_S_post_codeobject"
+    assert {"stdp_inputs_stateupdater_codeobject", "stdp_neurons_spike_thresholder_codeobject"} <= set(phases[0])
+    assert "grid barriers per step: 3" in src
