@@ -151,10 +151,18 @@ def _emulate_propagation(bn, blr, rows_len, nwarps, mode):
             nl = min(blr[L] - l0, b - a)
             a += nl
             n = rows_len[L][s]
-            rbeg = 0                # (alignment of the row start does not change the coverage)
-            lo, hi = rbeg + 32 * l0, min(n, rbeg + 32 * (l0 + nl))
-            for k in range(lo, hi):
-                visits[(L, s, k)] += 1
+            # the rows of a bin lie back to back in the CSR: the row starts at an arbitrary slot and
+            # the lines are the aligned 32-slot lines it touches ((len + 62) >> 5 always suffice)
+            rbeg = sum(rows_len[L][:s]) + 7 * L
+            rend = rbeg + n
+            abeg = (rbeg & ~31) + 32 * l0
+            end = min(rend, abeg + 32 * nl)
+            for lane in range(32):
+                k0 = abeg + lane
+                if k0 < rbeg:
+                    k0 += 32        # first line of the row: lanes in front of its start
+                for k in range(k0, end, 32):
+                    visits[(L, s, k - rbeg)] += 1
 
     if mode == "row":
         assert nrows <= nwarps
