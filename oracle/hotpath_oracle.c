@@ -6,7 +6,9 @@
  * known-answer tests for the spike queue (brian2/tests/test_spikequeue.py:36-61) and for delayed
  * delivery (brian2/tests/test_synapses.py:1154-1176), and (2) fixtures produced by running the
  * unmodified reference (cpp_standalone, serial, -ffp-contract=off) on the same inputs
- * (tests/golden/make_oracle_fixtures.py -> tests/golden/oracle_*.npz).
+ * (tests/golden/make_oracle_fixtures.py -> tests/golden/oracle_*.npz): LIF networks (CUBA,
+ * Brunel with heterogeneous delays), Song-Abbott STDP and the Hodgkin-Huxley network COBAHH --
+ * all bit-exact, spike trains and final state.
  *
  * Every function names the reference lines it restates (paths relative to brian2/ in
  * brian-team/brian2).  Plain C11, sequential, no FMA contraction (build with -ffp-contract=off).
@@ -305,4 +307,126 @@ long long oracle_stdp_run(int N_in, double* x, const double* rate, double* v1, d
     oq_destroy(qpre); oq_destroy(qpost);
     free(pre); free(post); free(ss_in);
     return n_in;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* COBAHH (examples/COBAHH.py:44-59 equations; BASELINE.json configs[1])                       */
+/* ------------------------------------------------------------------------------------------ */
+/* _exprel, codegen/generators/cpp_generator.py:603-611 */
+static double o_exprel(double x) {
+    if (fabs(x) < 1e-16) return 1.0;
+    if (x > 717) return INFINITY;
+    return expm1(x) / x;
+}
+
+/* One run of the Hodgkin-Huxley network of tests/models.py:cobahh: exponential-Euler state update
+ * (stateupdaters/exponential_euler.py:82: x <- -B/A + (B/A + x) exp(A dt) per variable, all from
+ * the OLD state; the grouping of the terms below is the one of the abstract code the reference
+ * generates for these equations -- rounding follows it), refractory threshold `v > -20 mV`
+ * without reset (templates/threshold.cpp:3-37 with `not_refractory`, `lastspike`), two delay-free
+ * pathways `ge += we` (sources [0, Ne)) and `gi += wi` (sources [Ne, N)) delivered in this order
+ * in the step of the spike (synapses_push_spikes.cpp:26-27, synapses.cpp:11-50), SpikeMonitor.
+ * par = { Cm, gl, El, EK, ENa, g_na, g_kd, VT, taue, taui, Ee, Ei, we, wi, refractory }. */
+long long oracle_hh_run(int N, int Ne, double* v, double* ge, double* gi, double* m, double* n,
+                        double* h, double* lastspike, char* not_refractory, const double* par,
+                        const int32_t* ce_pre, const int32_t* ce_post, int n_ce,
+                        const int32_t* ci_pre, const int32_t* ci_post, int n_ci,
+                        double dt, long long n_steps, int32_t* mon_i, double* mon_t,
+                        long long cap_spikes, int32_t* count, double* events_out) {
+    const double Cm = par[0], gl = par[1], El = par[2], EK = par[3], ENa = par[4], g_na = par[5],
+                 g_kd = par[6], VT = par[7], taue = par[8], taui = par[9], Ee = par[10], Ei = par[11],
+                 we = par[12], wi = par[13], refractory = par[14];
+    const double ms = 0.001, mV = 0.001;
+    /* loop-invariant scalars hoisted by codegen/optimisation.py (evaluated once per step there) */
+    const int64_t ref_steps = o_timestep(refractory, dt);
+    const double a_ge = exp(((-1.0) * dt) / taue), a_gi = exp(((-1.0) * dt) / taui);
+    const double k_ah = (0.128 * (2.5713844347880297 * exp((0.05555555555555555 * VT) / mV))) / ms;
+    const double s18 = 0.05555555555555555 / mV;
+    const double k_bh = (ms * 2980.9579870417283) * exp((0.2 * VT) / mV);
+    const double s5 = 0.2 / mV;
+    const double k_ah2 = (0.128 * (2.5713844347880297 * pow(exp(VT / mV), 0.05555555555555555))) / ms;
+    const double s1 = 1.0 / mV;
+    const double k_m = 1.28 / ms, k_mneg = (-1.28) / ms;
+    const double o_am = ((0.25 * VT) / mV) + 3.25, s4 = 0.25 / mV;
+    const double k_bm = 1.4 / ms;
+    const double o_bm = (-8.0) + ((0.2 * (-VT)) / mV);
+    const double k_an = 0.16 / ms;
+    const double k_bn = ((-0.6420127083438707) * pow(exp(VT / mV), 0.025)) / ms;
+    const double o_an = 3.0 + ((0.2 * VT) / mV);
+    const double c_l = (El * gl) / Cm, c_k = (EK * g_kd) / Cm, c_na = (ENa * g_na) / Cm;
+    const double c_e = Ee / Cm, c_i = Ei / Cm;
+    const double a_l = 0.0 - (gl / Cm), a_k = (-g_kd) / Cm, a_na = g_na / Cm, a_s = 1.0 / Cm;
+    /* per-source synapse lists in synapse-index order (CSpikeQueue::prepare, spikequeue.h:96-97) */
+    int* ce_ptr = (int*)calloc((size_t)N + 2, sizeof(int));
+    int* ci_ptr = (int*)calloc((size_t)N + 2, sizeof(int));
+    for (int k = 0; k < n_ce; ++k) ce_ptr[ce_pre[k] + 1]++;
+    for (int k = 0; k < n_ci; ++k) ci_ptr[ci_pre[k] + 1]++;
+    for (int i = 0; i < N; ++i) { ce_ptr[i + 1] += ce_ptr[i]; ci_ptr[i + 1] += ci_ptr[i]; }
+    int* ce_syn = (int*)malloc(sizeof(int) * (size_t)(n_ce > 0 ? n_ce : 1));
+    int* ci_syn = (int*)malloc(sizeof(int) * (size_t)(n_ci > 0 ? n_ci : 1));
+    {
+        int* cur = (int*)malloc(sizeof(int) * ((size_t)N + 1));
+        memcpy(cur, ce_ptr, sizeof(int) * ((size_t)N + 1));
+        for (int k = 0; k < n_ce; ++k) ce_syn[cur[ce_pre[k]]++] = k;
+        memcpy(cur, ci_ptr, sizeof(int) * ((size_t)N + 1));
+        for (int k = 0; k < n_ci; ++k) ci_syn[cur[ci_pre[k]]++] = k;
+        free(cur);
+    }
+    int32_t* spikes = (int32_t*)malloc(sizeof(int32_t) * (size_t)(N > 0 ? N : 1));
+    long long n_rec = 0;
+    double events = 0.0;
+    for (long long step = 0; step < n_steps; ++step) {
+        const double t = (double)step * dt;                           /* clocks.h:34-38 */
+        for (int i = 0; i < N; ++i) {                                 /* stateupdate.cpp:5-22 */
+            const double vi = v[i], gei = ge[i], gii = gi[i], mi = m[i], ni = n[i], hi = h[i];
+            not_refractory[i] = o_timestep(t - lastspike[i], dt) >= ref_steps;
+            const double new_ge = a_ge * gei, new_gi = a_gi * gii;
+            /* h:  A = -(alpha_h + beta_h), B/A as generated */
+            const double e5 = exp(s5 * (-vi));
+            const double p18 = pow(exp(s1 * vi), 0.05555555555555555);
+            const double A_h = ((-4.0) / (ms + (k_bh * e5))) - (k_ah2 / p18);
+            const double BA_h = (k_ah * exp(s18 * (-vi))) / A_h;
+            const double new_h = (-BA_h) + ((BA_h + hi) * exp(dt * A_h));
+            /* m */
+            const double x_am = o_exprel(o_am - (s4 * vi)), x_bm = o_exprel(o_bm + (s5 * vi));
+            const double A_m = (k_mneg / x_am) - (k_bm / x_bm);
+            const double BA_m = k_m / (A_m * x_am);
+            const double new_m = (-BA_m) + ((BA_m + mi) * exp(dt * A_m));
+            /* n */
+            const double p40 = pow(exp(s1 * vi), 0.025), x_an = o_exprel(o_an - (s5 * vi));
+            const double A_n = (k_bn / p40) - (k_an / x_an);
+            const double BA_n = k_an / (A_n * x_an);
+            const double new_n = (-BA_n) + ((BA_n + ni) * exp(dt * A_n));
+            /* v */
+            const double n4 = pow(ni, 4), m3 = pow(mi, 3);
+            const double A_v = (a_l + (a_k * n4)) - (((a_na * (hi * m3)) + (a_s * gei)) + (a_s * gii));
+            const double B_v = c_l + ((((c_k * n4) + (c_na * (hi * m3))) + (c_e * gei)) + (c_i * gii));
+            const double BA_v = B_v / A_v;
+            const double new_v = (-BA_v) + ((BA_v + vi) * exp(dt * A_v));
+            ge[i] = new_ge; gi[i] = new_gi; h[i] = new_h; m[i] = new_m; n[i] = new_n; v[i] = new_v;
+        }
+        int ns = 0;                                                   /* threshold.cpp:18-31 */
+        for (int i = 0; i < N; ++i) {
+            const int cond = not_refractory[i] ? (v[i] > (-20.0) * mV) : 0;
+            if (cond) { spikes[ns++] = i; not_refractory[i] = 0; lastspike[i] = t; }
+        }
+        for (int s = 0; s < ns; ++s) {                                /* spikemonitor.cpp:6-51 */
+            if (n_rec < cap_spikes) { mon_i[n_rec] = spikes[s]; mon_t[n_rec] = t; }
+            n_rec++;
+            count[spikes[s]]++;
+        }
+        for (int s = 0; s < ns; ++s) {                                /* hh_Ce: ge += we */
+            const int src = spikes[s];
+            if (src >= Ne) continue;
+            for (int k = ce_ptr[src]; k < ce_ptr[src + 1]; ++k) { ge[ce_post[ce_syn[k]]] += we; events += 1.0; }
+        }
+        for (int s = 0; s < ns; ++s) {                                /* hh_Ci: gi += wi */
+            const int src = spikes[s];
+            if (src < Ne) continue;
+            for (int k = ci_ptr[src]; k < ci_ptr[src + 1]; ++k) { gi[ci_post[ci_syn[k]]] += wi; events += 1.0; }
+        }
+    }
+    if (events_out) *events_out = events;
+    free(ce_ptr); free(ci_ptr); free(ce_syn); free(ci_syn); free(spikes);
+    return n_rec;
 }

@@ -205,3 +205,33 @@ def stdp_run(x, rate, w, par, dt, n_steps, v0):
     assert n_in <= cap_in
     return dict(w=w, Apre=Apre, Apost=Apost, lastupdate=lastupdate, v=v1, ge=ge1, x=x,
                 in_spikes_i=in_i[:n_in], in_spikes_t=in_t[:n_in], spikes_t=out_t[:n_out.value])
+
+
+def hh_run(state, par, ce, ci, dt, n_steps, Ne):
+    """COBAHH network of tests/models.py:cobahh.  ``state``: dict v, ge, gi, m, n, h (initial);
+    ``par``: dict of the namespace (floats in SI units) + 'refractory'; ``ce``/``ci``: (pre, post)
+    absolute indices.  Returns the final state and the spike monitor."""
+    N = len(state["v"])
+    s = {k: np.array(state[k], dtype=np.float64) for k in ("v", "ge", "gi", "m", "n", "h")}
+    lastspike = np.full(N, -1e4)
+    not_refractory = np.ones(N, dtype=np.int8)
+    p = np.array([par[k] for k in ("Cm", "gl", "El", "EK", "ENa", "g_na", "g_kd", "VT", "taue", "taui",
+                                   "Ee", "Ei", "we", "wi", "refractory")], dtype=np.float64)
+    ce_pre, ce_post = (np.ascontiguousarray(a, dtype=np.int32) for a in ce)
+    ci_pre, ci_post = (np.ascontiguousarray(a, dtype=np.int32) for a in ci)
+    cap = max(4096, N * n_steps // 50)
+    mon_i, mon_t = np.zeros(cap, dtype=np.int32), np.zeros(cap)
+    count = np.zeros(N, dtype=np.int32)
+    events = ctypes.c_double(0.0)
+    L = lib()
+    L.oracle_hh_run.restype = ctypes.c_longlong
+    nrec = L.oracle_hh_run(
+        ctypes.c_int(N), ctypes.c_int(Ne), _d(s["v"]), _d(s["ge"]), _d(s["gi"]), _d(s["m"]), _d(s["n"]),
+        _d(s["h"]), _d(lastspike), not_refractory.ctypes.data_as(ctypes.c_char_p), _d(p),
+        _i(ce_pre), _i(ce_post), ctypes.c_int(len(ce_pre)), _i(ci_pre), _i(ci_post), ctypes.c_int(len(ci_pre)),
+        ctypes.c_double(dt), ctypes.c_longlong(n_steps), _i(mon_i), _d(mon_t), ctypes.c_longlong(cap),
+        _i(count), ctypes.byref(events))
+    assert nrec <= cap
+    out = dict(s)
+    out.update(spikes_i=mon_i[:nrec], spikes_t=mon_t[:nrec], spikes_count=count, events=events.value)
+    return out

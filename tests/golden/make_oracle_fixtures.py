@@ -28,6 +28,7 @@ CASES = {
     "oracle_cuba_400": ("cuba", dict(N=400, p=0.1, duration=0.1)),
     "oracle_brunel_500": ("brunel", dict(N_E=400, epsilon=0.1, duration=0.1, hetero_delays=True)),
     "oracle_stdp_200": ("stdp", dict(N=200, duration=0.3)),
+    "oracle_cobahh_300": ("cobahh", dict(N=300, duration=0.1, n_syn_per_neuron=30.0, trace=())),
 }
 
 
@@ -49,8 +50,10 @@ def _inputs(objs):
     return out
 
 
-def main():
+def main(names=None):
     for case, (model, kwds) in CASES.items():
+        if names and case not in names:
+            continue
         kw0 = dict(kwds, duration=0.0)
         objs0, _ = models.run_model(b, model, "cpp_standalone", tempfile.mkdtemp(prefix=case), **kw0)
         data = _inputs(objs0)
@@ -67,4 +70,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

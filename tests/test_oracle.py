@@ -147,3 +147,30 @@ def test_stdp_fixture_bit_exact():
     assert np.array_equal(r["w"], g["S_w"])
     assert np.array_equal(r["v"], g["neurons_v"])
     assert np.array_equal(r["ge"], g["neurons_ge"])
+
+
+def test_cobahh_fixture_bit_exact():
+    """BASELINE configs[1] family: the Hodgkin-Huxley network (exponential Euler, exprel rate
+    functions, refractory threshold without reset, two delay-free conductance pathways) restated
+    in C against the unmodified reference's cpp_standalone run of the same inputs: spike train
+    identical and -- same libm, same grouping of the terms -- state bit-identical."""
+    g = _load("oracle_cobahh_300")
+    n_steps = int(round(float(g["duration"][0]) / DT))
+    N = len(g["in_P_v"])
+    ms = mV = 0.001
+    um, cm, uF, siemens, msiemens, nS = 1e-6, 0.01, 1e-6, 1.0, 0.001, 1e-9
+    area = 20000 * um ** 2
+    par = dict(Cm=(1 * uF * cm ** -2) * area, gl=(5e-5 * siemens * cm ** -2) * area, El=-60 * mV, EK=-90 * mV,
+               ENa=50 * mV, g_na=(100 * msiemens * cm ** -2) * area, g_kd=(30 * msiemens * cm ** -2) * area,
+               VT=-63 * mV, taue=5 * ms, taui=10 * ms, Ee=0 * mV, Ei=-80 * mV, we=6 * nS, wi=67 * nS,
+               refractory=3 * ms)
+    state = {k: g["in_P_" + k] for k in ("v", "ge", "gi", "m", "n", "h")}
+    r = ho.hh_run(state, par, (g["in_Ce_pre"], g["in_Ce_post"]), (g["in_Ci_pre"], g["in_Ci_post"]), DT,
+                  n_steps, Ne=int(0.8 * N))
+    assert len(g["spikes_i"]) > 100
+    assert np.array_equal(r["spikes_i"], g["spikes_i"])
+    assert np.array_equal(r["spikes_t"], g["spikes_t"])
+    assert np.array_equal(r["spikes_count"], g["spikes_count"])
+    for k in ("v", "ge", "gi", "m", "n", "h"):
+        np.testing.assert_allclose(r[k], g["P_" + k], rtol=1e-12, atol=0, err_msg=k)
+        assert np.array_equal(r[k], g["P_" + k]), k
