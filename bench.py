@@ -39,8 +39,14 @@ WORKLOADS = {
     "cuba_256k": ("cuba", dict(N=256000, p=80.0 / 256000), 58.0, 20.0),
     "brunel_100k": ("brunel", dict(N_E=80000, epsilon=0.01, deterministic=True), 33.0, 20.0),
     # BASELINE configs[2] per GPU: 125k neurons x 1000 synapses each; `--gpus 8` = 1M neurons / 1B
-    # synapses, heterogeneous delays 1..20 steps, partitioned by postsynaptic neuron
+    # synapses, heterogeneous delays 1..20 steps, partitioned by postsynaptic neuron.
+    # brunel_125k: connectivity by the reference's host connect() (bit-identical to cpp_standalone;
+    # every rank builds the whole network); brunel_125k_sharded: every rank creates the synapses of
+    # its own neurons on the device (prefs.devices.b200.construction = 'sharded') -- the only way
+    # to the 10^9-synapse network
     "brunel_125k": ("brunel", dict(N_E=100000, epsilon=0.008, deterministic=True), 33.0, 20.0),
+    "brunel_125k_sharded": ("brunel", dict(N_E=100000, epsilon=0.008, deterministic=True), 33.0, 20.0),
+    "brunel_125k_poisson": ("brunel", dict(N_E=100000, epsilon=0.008, deterministic=False), 33.0, 20.0),
     # BASELINE configs[3]: Song-Abbott STDP, 100k plastic synapses onto one neuron (on_pre 84 B,
     # on_post 68 B per event; regular-firing inputs instead of Poisson so that it is deterministic)
     "stdp_100k": ("stdp", dict(N=100000), 0.0, 84.0),
@@ -55,11 +61,27 @@ WORKLOADS = {
     "synapses_only_highrate": ("synapses_only", dict(N=100000, p=0.2, rate_hz=100.0), 0.0, 20.0),
 }
 
+#: device preferences of a workload (everything else runs with the defaults)
+WORKLOAD_PREFS = {
+    "brunel_125k_sharded": {"devices.b200.construction": "sharded"},
+    "brunel_125k_poisson": {"devices.b200.construction": "sharded"},
+}
+
+#: extra configurations measured after the headline workload in a default run (no --workload):
+#: BASELINE.json configs[2], the north-star network (N GPUs x 125k neurons / 125M synapses)
+EXTRA_CONFIGS = ["brunel_125k_sharded"]
 
 # simulation timesteps (dt = 0.1 ms) of one bench step = one run() call
 DEFAULT_SIM_STEPS = {"cobahh_256k": 4000, "cuba_256k": 4000, "cuba_4k": 10000, "cobahh_4k": 10000,
-                     "brunel_100k": 2000, "brunel_125k": 1000, "stdp_100k": 5000, "potjans_77k": 1000, "potjans_8k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
+                     "brunel_100k": 2000, "brunel_125k": 1000, "brunel_125k_sharded": 1000,
+                     "brunel_125k_poisson": 1000, "stdp_100k": 5000, "potjans_77k": 1000,
+                     "potjans_8k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
                      "synapses_only_highrate": 500}
+
+# timesteps per step of the reference arm (CPU): bounded so that 25 steps end within minutes
+REFERENCE_SIM_STEPS = {"cobahh_256k": 500, "cuba_256k": 2000, "brunel_125k": 50, "brunel_125k_sharded": 50,
+                       "brunel_100k": 50, "potjans_77k": 20, "synapses_only_highrate": 10,
+                       "synapses_only_sparse": 50, "synapses_only_dense": 50}
 
 
 def _n_neurons(objs):
@@ -232,13 +254,26 @@ def _outdegree_events(b, objs, t_from):
     return total, nspikes
 
 
-def run_b200(args, rank, world):
+def _apply_prefs(b, workload, reset=False):
+    defaults = {"devices.b200.construction": "reference"}
+    for key, value in defaults.items():
+        b.prefs[key] = value
+    if not reset:
+        for key, value in WORKLOAD_PREFS.get(workload, {}).items():
+            b.prefs[key] = value
+
+
+def run_b200(args, rank, world, workload=None, steps=None, warmup=None, sim_steps=None):
+    """Build + run one workload on the b200 device; returns the measurements of this rank."""
     b = _import_brian()
+    workload = workload or args.workload
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     if world > 1:
         _barrier(world)   # initialises the process group: the device shards over its ranks
-    sim_steps = args.sim_steps or DEFAULT_SIM_STEPS.get(args.workload, 2000)
-    n_runs = args.warmup + args.steps
-    directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"bench_{args.workload}_r{rank}")
+    sim_steps = sim_steps or args.sim_steps or DEFAULT_SIM_STEPS.get(workload, 2000)
+    n_runs = warmup + steps
+    directory = _project_dir(f"bench_{workload}_w{1 if args.replicas else world}", rank)
     t_build0 = time.time()
     b.prefs["devices.b200.multi_gpu"] = not args.replicas
     b.prefs["devices.b200.persistent"] = not args.stepwise
@@ -247,30 +282,37 @@ def run_b200(args, rank, world):
         b.prefs["devices.b200.ctas_per_sm"] = args.ctas_per_sm
     if args.grid:
         b.prefs["devices.b200.grid"] = args.grid
+    _apply_prefs(b, workload)
     scale = 1 if args.replicas else world
-    objs = _build_script(b, args.workload, "b200", directory, sim_steps, n_runs, scale=scale)
-    b.device.build(directory=directory, compile=True, run=False, with_output=False)
+    try:
+        objs = _build_script(b, workload, "b200", directory, sim_steps, n_runs, scale=scale)
+        b.device.build(directory=directory, compile=True, run=False, with_output=False)
+    finally:
+        sharded = b.prefs["devices.b200.construction"] == "sharded"
+        _apply_prefs(b, workload, reset=True)
     build_seconds = time.time() - t_build0
 
     _barrier(world)
     sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
-    t0 = time.time()
+    t_run0 = time.time()
     b.device.run(directory=directory, with_output=False)
-    t1 = time.time()
+    run_wall = time.time() - t_run0
     cnt = b.device.counter
     runs = int(cnt("runs"))
     assert runs == n_runs, (runs, n_runs)
-    timed = range(args.warmup, n_runs)
+    timed = range(warmup, n_runs)
     clocks = sampler.stop([(cnt(f"run{r}.t0_unix"), cnt(f"run{r}.t0_unix") + cnt(f"run{r}.wall_seconds"))
                            for r in timed])
     dev_s = sum(cnt(f"run{r}.device_seconds") for r in timed)
-    e2e_s = sum(cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds") + cnt(f"run{r}.download_seconds")
-                for r in timed)
+    # end to end = what a user's run() call costs: (re)build of the pathway CSRs if the host
+    # arrays changed + upload + step loop + download
+    e2e_s = sum(cnt(f"run{r}.prepare_seconds") + cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds")
+                + cnt(f"run{r}.download_seconds") for r in timed)
     e2e_parts = {k: 1e3 * sum(cnt(f"run{r}.{k}_seconds") for r in timed) / max(len(timed), 1)
-                 for k in ("upload", "wall", "download")}
+                 for k in ("prepare", "upload", "wall", "download")}
     events = sum(cnt(f"run{r}.events") for r in timed)
-    steps = sum(cnt(f"run{r}.steps") for r in timed)
+    nsteps = sum(cnt(f"run{r}.steps") for r in timed)
     persistent = all(cnt(f"run{r}.persistent") == 1 for r in timed)
     if args.phases and world > 1:
         n = max(cnt("polls"), 1.0)
@@ -281,36 +323,144 @@ def run_b200(args, rank, world):
         for name, cycs in b.device.phase_profile(all_ctas=True):
             cols = " ".join(f"{c / total_steps / 1.965e3:8.3f}" for c in cycs)
             sys.stderr.write(f"PHASE r{rank} {name:55s} {cols}  us/step (CTA 0, 1/4, 3/4, last)\n")
-    model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
+    model, kwds, bytes_neuron, bytes_event = WORKLOADS[workload]
     n_neurons = _n_neurons(objs)
-    n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
-    return dict(dev_s=dev_s, e2e_s=e2e_s, events=events, timesteps=steps, persistent=persistent,
+    # synapses: of the whole network (sharded construction: the ranks' counts are added up by the caller)
+    n_syn_local = sum(int(np_len(o)) for o in objs.values() if isinstance(o, b.Synapses)) if not sharded \
+        else int(cnt("connect_synapses"))
+    return dict(dev_s=dev_s, e2e_s=e2e_s, events=events, timesteps=nsteps, persistent=persistent,
                 h2d=cnt("h2d_bytes") / n_runs, d2h=cnt("d2h_bytes") / n_runs, launches=cnt("launches"),
-                clocks=clocks, n_neurons=n_neurons, n_syn=n_syn, build_seconds=build_seconds,
+                clocks=clocks, n_neurons=n_neurons, n_syn=n_syn_local, sharded=sharded,
+                build_seconds=build_seconds, run_wall=run_wall,
+                connect_seconds=cnt("connect_seconds"), prepare_seconds=cnt("prepare_seconds"),
                 sim_steps=sim_steps, bytes_neuron=bytes_neuron, bytes_event=bytes_event, e2e_parts=e2e_parts,
-                spikes=len(objs["spikes"].i[:]) if "spikes" in objs else None)
+                objs=objs, workload=workload, steps=steps, warmup=warmup, grid=int(cnt("grid")))
 
 
-def run_reference(args, sim_steps, warmup, steps, threads, strict=False):
+def _project_dir(name, rank):
+    """In-tree project directory of this rank.  The generated sources do not depend on the rank:
+    a rank without a directory of its own starts from a copy of rank 0's (if that was built
+    ahead, e.g. by tools/prebuild_bench.py), so that `make` finds nothing to do."""
+    import shutil
+
+    base = os.path.join(ROOT, "brian2_b200", "_prebuilt")
+    mine, first = os.path.join(base, f"{name}_r{rank}"), os.path.join(base, f"{name}_r0")
+    if rank > 0 and not os.path.isdir(mine) and os.path.exists(os.path.join(first, "libb200_project.so")):
+        shutil.copytree(first, mine, ignore=shutil.ignore_patterns("results", "libb200_project_run*"))
+    return mine
+
+
+def np_len(obj):
+    try:
+        return len(obj)
+    except Exception:
+        return 0
+
+
+def run_reference(args, sim_steps, warmup, steps, threads, strict=False, workload=None, scale=1):
     """The reference's own CPU implementation of the path (cpp_standalone [+ OpenMP])."""
     b = _import_brian()
+    workload = workload or args.workload
     n_runs = warmup + steps
     directory = tempfile.mkdtemp(prefix="b200_bench_ref_")
-    objs = _build_script(b, args.workload, "cpp_standalone", directory, sim_steps, n_runs,
-                         openmp_threads=threads, strict=strict)
+    _apply_prefs(b, workload, reset=True)
+    objs = _build_script(b, workload, "cpp_standalone", directory, sim_steps, n_runs,
+                         openmp_threads=threads, strict=strict, scale=scale)
     b.device.build(directory=directory, compile=True, run=True, with_output=False)
     with open(os.path.join(b.device.results_dir, "stdout.txt")) as f:
         times = [float(line.split()[1]) for line in f if line.startswith("B200BENCH_RUN")]
     assert len(times) == n_runs, (times, n_runs)
     loop_s = sum(times[warmup:])
+    n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
     if "spikes" in objs:
         events, nspikes = _outdegree_events(b, objs, warmup * sim_steps * 1e-4)
     else:   # SynapsesOnly: every source spikes every step, so every synapse carries one event per step
-        n_syn = sum(len(o) for o in objs.values() if isinstance(o, b.Synapses))
         events, nspikes = float(n_syn) * steps * sim_steps, None
     n_neurons = _n_neurons(objs)
     return dict(loop_s=loop_s, events=events, timesteps=steps * sim_steps, n_neurons=n_neurons,
-                spikes=nspikes)
+                spikes=nspikes, n_syn=n_syn, objs=objs)
+
+
+# ---------------------------------------------------------------------------------------------
+# parity checks carried by the bench line (outside every timed region)
+# ---------------------------------------------------------------------------------------------
+def parity_prefix_vs_reference(args, r, n_check=200):
+    """1 GPU: the first `n_check` timesteps of the network that was just benchmarked, run again on
+    the reference's cpp_standalone (serial, strict floating-point flags): the spike trains (i, t)
+    must be identical."""
+    import numpy as np
+
+    b = _import_brian()
+    mon = r["objs"].get("spikes")
+    if mon is None:
+        return {"checked": False, "why": "workload has no SpikeMonitor"}
+    t_end = n_check * 1e-4 - 1e-9
+    i_dev, t_dev = np.asarray(mon.i[:]), np.asarray(mon.t_[:])
+    sel = t_dev < t_end
+    i_dev, t_dev = i_dev[sel].copy(), t_dev[sel].copy()
+    ref = run_reference(args, n_check, 0, 1, 0, strict=True, workload=r["workload"])
+    mon_ref = ref["objs"]["spikes"]
+    i_ref, t_ref = np.asarray(mon_ref.i[:]), np.asarray(mon_ref.t_[:])
+    same = bool(i_dev.shape == i_ref.shape and np.array_equal(i_dev, i_ref) and np.array_equal(t_dev, t_ref))
+    first_diff = None
+    if not same:
+        n = min(len(i_dev), len(i_ref))
+        bad = np.nonzero((i_dev[:n] != i_ref[:n]) | (t_dev[:n] != t_ref[:n]))[0]
+        first_diff = float(t_ref[bad[0]]) if len(bad) else float(min(t_dev[n - 1] if n else 0.0, t_ref[n - 1] if n else 0.0))
+    return {"checked": True, "identical": same, "timesteps": n_check, "spikes_compared": int(len(i_ref)),
+            "against": "the reference's cpp_standalone (serial, -O3 -ffp-contract=off) on the same network, "
+                       "same seed: spike trains (i, t) of the first timesteps", "first_difference_t": first_diff}
+
+
+def parity_multi_gpu(args, rank, world):
+    """N > 1: (a) golden cases (reference connectivity) partitioned over the N ranks must reproduce
+    the reference's spike trains; (b) a reduced Brunel network built per rank on the device must
+    give, on N GPUs, exactly what rank 0 computes alone."""
+    import numpy as np
+
+    b = _import_brian()
+    import models
+    from golden.make_golden import CASES
+
+    out = {"checked": True, "n_gpus": world, "cases": {}}
+    ok = True
+    for case in ("brunel_hetero", "cuba_1000"):
+        model, kwds = CASES[case]
+        d = _project_dir(f"bench_parity_{case}", rank)
+        objs, res = models.run_model(b, model, "b200", d, **kwds)
+        gold = np.load(os.path.join(ROOT, "tests", "golden", f"{case}.npz"))
+        same = all(np.array_equal(gold[k], res[k]) for k in gold.files)
+        out["cases"][case] = {"identical_to_reference_golden": bool(same), "spikes": int(len(res["spikes_i"]))}
+        ok = ok and same
+        _barrier(world)
+    # sharded construction: N ranks against one rank
+    model, kwds = "brunel", dict(N_E=8000, epsilon=0.0125, duration=0.03)
+    runs = {}
+    for mode in ("ranks", "single"):
+        if mode == "single" and rank != 0:
+            continue
+        d = _project_dir("bench_parity_sharded", rank)
+        try:
+            objs, res = models.run_model(b, model, "b200", d,
+                                         prefs_update={"devices.b200.construction": "sharded",
+                                                       "devices.b200.multi_gpu": mode == "ranks"}, **kwds)
+        finally:
+            b.prefs["devices.b200.construction"] = "reference"
+            b.prefs["devices.b200.multi_gpu"] = not args.replicas
+        res["exc_i"], res["exc_j"] = np.asarray(objs["exc"].i[:]), np.asarray(objs["exc"].j[:])
+        res["exc_delay"] = np.asarray(objs["exc"].delay_[:])
+        runs[mode] = res
+    if rank == 0:
+        keys = [k for k in runs["single"] if k != "last_run_time"]
+        same = all(runs["single"][k].shape == runs["ranks"][k].shape and
+                   np.array_equal(runs["single"][k], runs["ranks"][k]) for k in keys)
+        out["cases"]["brunel_10k_sharded_construction"] = {
+            "identical_to_1_gpu": bool(same), "spikes": int(len(runs["single"]["spikes_i"])),
+            "synapses": int(runs["single"]["exc_nsyn"][0] + runs["single"]["inh_nsyn"][0])}
+        ok = ok and same
+    _barrier(world)
+    out["identical"] = bool(ok)
+    return out
 
 
 def _dist():
@@ -359,15 +509,93 @@ def _allreduce(values, op, world):
     return t.tolist()
 
 
+def _config(workload, n_neurons, n_syn, sharded):
+    model, kwds, _, _ = WORKLOADS[workload]
+    return {
+        "workload": f"{workload}: {model} {kwds}, dt=0.1ms, fp64, "
+                    + ("SpikeMonitor + StateMonitor of 3 voltage traces" if model == "cobahh" else
+                       "no monitors" if model == "synapses_only" else "SpikeMonitor(s)"),
+        "neurons": int(n_neurons), "synapses": int(n_syn),
+        "connectivity": ("created per rank on the device (one Philox stream per source row, "
+                         "csrc/b200_connect.cuh); statistically equivalent to the reference's connect()"
+                         if sharded else
+                         "reference Synapses.connect (host, mt19937), identical on both arms"),
+        "l2": "no explicit flush: a bench step is one run() of thousands of simulation timesteps over the "
+              "same state and CSR (a simulation re-reads its working set every timestep by nature; whether "
+              "it is L2 resident is a property of the workload: COBAHH-256k state 14 MB + CSR 82 MB vs "
+              "126 MB of L2); every timed step starts after the H2D upload of the state arrays",
+    }
+
+
+def _b200_line(args, r, world, hbm_peak, peak_src):
+    """Whole-job JSON line of one measured workload (call on every rank; returns None off rank 0)."""
+    rank, _ = _dist()
+    dev_s, e2e_s = _allreduce([r["dev_s"], r["e2e_s"]], "MAX", world)
+    sums = [r["events"]] + ([float(r["n_syn"])] if r["sharded"] else [])
+    sums = _allreduce(sums, "SUM", world)
+    events = sums[0]
+    n_syn = int(sums[1]) if r["sharded"] else r["n_syn"]
+    if rank != 0:
+        return None
+    steps, warmup = r["steps"], r["warmup"]
+    timesteps = r["timesteps"]
+    bytes_neuron, bytes_event = r["bytes_neuron"], r["bytes_event"]
+    # per-GPU roofline (rank 0): the neurons it owns and the synaptic events it delivered
+    n_owned = r["n_neurons"] / (1 if (args.replicas or world == 1) else world)
+    algo_bytes = timesteps * n_owned * bytes_neuron + r["events"] * bytes_event
+    achieved = algo_bytes / r["dev_s"] / 1e9
+    prop_bytes = r["events"] * bytes_event
+    line = {
+        "metric": "synaptic_events_per_s", "value": events / dev_s, "unit": "events/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": _config(r["workload"], r["n_neurons"], n_syn, r["sharded"]),
+        "timesteps_per_step": r["sim_steps"],
+        "parallelism": "1 GPU" if world == 1 else (
+            f"{world} independent replicas (one per GPU)" if args.replicas else
+            f"one network of {world}x the neurons (same synapses per neuron) partitioned by postsynaptic "
+            f"neuron over {world} GPUs; spike lists exchanged by NVLink peer stores inside the persistent kernel"),
+        "execution": ("persistent cooperative step kernel" if r["persistent"] else "one launch per code object")
+                     + f", {r['grid']} CTAs x 512 threads",
+        "host_seconds": {"codegen_and_build": round(r["build_seconds"], 1), "device_run_call": round(r["run_wall"], 1),
+                         "synapse_creation_on_device": round(r["connect_seconds"], 3),
+                         "pathway_csr_build": round(r["prepare_seconds"], 2)},
+        "realtime_factor": timesteps * 1e-4 / dev_s,
+        "us_per_timestep": 1e6 * dev_s / max(timesteps, 1),
+        "events_per_timestep": events / max(timesteps, 1),
+        "clocks": r["clocks"],
+        "e2e": {"value": events / e2e_s, "unit": "events/s", "h2d_bytes_per_step": r["h2d"],
+                "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": {"pathway_csr_build": r["e2e_parts"]["prepare"], "upload": r["e2e_parts"]["upload"],
+                                "loop_host_clock": r["e2e_parts"]["wall"], "download": r["e2e_parts"]["download"]}},
+        "gpu_launches": int(r["launches"]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": _ncu_traffic(r["workload"], r["sim_steps"]),
+                     "traffic_source": "profiles/ncu_traffic.json: DRAM bytes of an `ncu --set full` capture of "
+                                       "the same workload, scaled to the timesteps of a launch (not this run)",
+                     "algorithmic_bytes_per_launch": algo_bytes / max(steps, 1),
+                     "peak_source": peak_src,
+                     "kernel": "persistent step kernel (stateupdate+threshold+propagation+monitors)",
+                     "algorithmic_bytes": f"{bytes_neuron} B/neuron-step + {bytes_event} B/event",
+                     "propagation_only": {"achieved": prop_bytes / r["dev_s"] / 1e9,
+                                          "frac": prop_bytes / r["dev_s"] / 1e9 / hbm_peak,
+                                          "note": "events x bytes/event over the WHOLE step time (state update, "
+                                                  "barriers and monitors included), per GPU"}},
+    }
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cobahh_256k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--sim-steps", type=int, default=0, help="simulation timesteps per bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="default run: skip the extra configurations (Brunel) and the parity checks")
     ap.add_argument("--replicas", action="store_true",
                     help="N>1: every rank simulates its own copy of the network instead of sharding one "
                          "N-times larger network over the ranks")
@@ -378,36 +606,31 @@ def main():
     ap.add_argument("--stepwise", action="store_true",
                     help="profiling aid: one kernel launch per code object per step (not the product mode)")
     args = ap.parse_args()
+    default_run = args.workload is None
+    if default_run:
+        args.workload = "cobahh_256k"
     rank, world = _dist()
     hbm_peak, peak_src = _peaks()
-    model, kwds, bytes_neuron, bytes_event = WORKLOADS[args.workload]
-    config = {
-        "workload": f"{args.workload}: {model} {kwds}, dt=0.1ms, fp64, "
-                    + ("SpikeMonitor + StateMonitor of 3 voltage traces" if model == "cobahh" else
-                       "no monitors" if model == "synapses_only" else "SpikeMonitor(s)"),
-        "connectivity": "reference Synapses.connect (host, mt19937), identical on both arms",
-        "l2": "no explicit flush: a bench step is one run() of thousands of simulation timesteps over the "
-              "same state and CSR (a simulation re-reads its working set every timestep by nature; whether "
-              "it is L2 resident is a property of the workload: COBAHH-256k state 14 MB + CSR 82 MB vs "
-              "126 MB of L2); every timed step starts after the H2D upload of the state arrays",
-    }
 
     if args.impl == "reference":
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        sim_steps = args.sim_steps or 500
-        r = run_reference(args, sim_steps, args.warmup, args.steps, threads, strict=False)
+        scale = 1 if args.replicas else max(1, args.gpus)
+        sim_steps = args.sim_steps or max(10, REFERENCE_SIM_STEPS.get(args.workload, 500) // scale)
+        r = run_reference(args, sim_steps, args.warmup, args.steps, threads, strict=False, scale=scale)
         value = r["events"] / r["loop_s"]
-        config["timesteps_per_step"] = sim_steps
         line = {
             "impl": "reference", "metric": "synaptic_events_per_s", "value": value, "unit": "events/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["loop_s"] / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(args.workload, r["n_neurons"], r["n_syn"], False),
+            "timesteps_per_step": sim_steps,
             "realtime_factor": r["timesteps"] * 1e-4 / r["loop_s"],
             "cpu_baseline": {"value": value, "unit": "events/s", "cores": threads, "kind": "reference",
-                             "sample": f"{args.steps} x {sim_steps} timesteps of the same network, "
+                             "sample": f"{args.steps} x {sim_steps} timesteps of the same network "
+                                       f"({r['n_neurons']} neurons, {r['n_syn']} synapses), "
                                        f"cpp_standalone + OpenMP({threads}), reference default flags"},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -415,50 +638,31 @@ def main():
         return
 
     r = run_b200(args, rank, world)
-    # whole-job numbers: max time over ranks, events summed over ranks
-    dev_s, e2e_s = _allreduce([r["dev_s"], r["e2e_s"]], "MAX", world)
-    events, = _allreduce([r["events"]], "SUM", world)
+    line = _b200_line(args, r, world, hbm_peak, peak_src)
+    extras, parity = [], None
+    if default_run and not args.no_extra:
+        # parity of the benchmarked configuration (1 GPU) / of the partitioned execution (N GPUs)
+        try:
+            parity = parity_prefix_vs_reference(args, r) if world == 1 else parity_multi_gpu(args, rank, world)
+        except Exception as ex:   # a failed check must be visible, never hide the measurement
+            parity = {"checked": False, "why": f"{type(ex).__name__}: {ex}"}
+        for name in EXTRA_CONFIGS:
+            try:
+                rx = run_b200(args, rank, world, workload=name, steps=min(args.steps, 10), warmup=min(args.warmup, 3))
+                extra = _b200_line(args, rx, world, hbm_peak, peak_src)
+            except Exception as ex:
+                extra = {"config": {"workload": name}, "error": f"{type(ex).__name__}: {ex}"}
+            if extra is not None:
+                extras.append(extra)
     if rank != 0:
         return
-    value = events / dev_s
-    e2e_value = events / e2e_s
-    timesteps = r["timesteps"]
-    # per-GPU roofline (rank 0): the neurons it owns and the synaptic events it delivered
-    n_owned = r["n_neurons"] / (1 if (args.replicas or world == 1) else world)
-    algo_bytes = timesteps * n_owned * bytes_neuron + r["events"] * bytes_event
-    achieved = algo_bytes / r["dev_s"] / 1e9
-    config.update({
-        "timesteps_per_step": r["sim_steps"], "neurons": r["n_neurons"], "synapses": r["n_syn"],
-        "parallelism": "1 GPU" if world == 1 else (
-            f"{world} independent replicas (one per GPU)" if args.replicas else
-            f"one network of {world}x the neurons (same synapses per neuron) partitioned by postsynaptic "
-            f"neuron over {world} GPUs; spike lists exchanged by NVLink peer stores inside the persistent kernel"),
-        "execution": "persistent cooperative step kernel" if r["persistent"] else "one launch per code object",
-        "build_seconds": round(r["build_seconds"], 1),
-    })
-    line = {
-        "metric": "synaptic_events_per_s", "value": value, "unit": "events/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config,
-        "realtime_factor": timesteps * 1e-4 / dev_s,
-        "us_per_timestep": 1e6 * dev_s / max(timesteps, 1),
-        "clocks": r["clocks"],
-        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": r["h2d"],
-                "d2h_bytes_per_step": r["d2h"],
-                "ms_per_step": {"upload": r["e2e_parts"]["upload"], "loop_host_clock": r["e2e_parts"]["wall"],
-                                "download": r["e2e_parts"]["download"]}},
-        "gpu_launches": int(r["launches"]),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": _ncu_traffic(args.workload, r["sim_steps"]),
-                     "algorithmic_bytes_per_launch": algo_bytes / max(args.steps, 1),
-                     "peak_source": peak_src,
-                     "kernel": "persistent step kernel (stateupdate+threshold+propagation+monitors)",
-                     "algorithmic_bytes": f"{bytes_neuron} B/neuron-step + {bytes_event} B/event"},
-    }
+    if parity is not None:
+        line["parity_check"] = parity
+    if extras:
+        line["configs"] = extras
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        ref_steps = 50 if "256k" in args.workload else 2000
+        ref_steps = 50 if "256k" in args.workload else REFERENCE_SIM_STEPS.get(args.workload, 2000)
         try:
             ref = run_reference(args, ref_steps, 1, 2, threads, strict=False)
             line["cpu_baseline"] = {

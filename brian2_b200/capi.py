@@ -39,17 +39,27 @@ class B200Library:
     for free by starting a new process for every run)."""
 
     _copies = 0
+    #: paths this process has already dlopen()ed.  glibc matches loaded objects by NAME and ctypes
+    #: never dlclose()s, so opening a rebuilt library under a path that was loaded before would
+    #: silently return the OLD code and static state: every repeat gets a private copy.
+    _loaded_paths = set()
 
     def __init__(self, path, fresh_copy=False):
         path = os.path.abspath(path)
         if not os.path.exists(path):
             raise RuntimeError(f"b200 project library not found: {path} (build failed?)")
-        if fresh_copy:
+        if fresh_copy or path in B200Library._loaded_paths:
             B200Library._copies += 1
             base, ext = os.path.splitext(path)
             copy = f"{base}_run{B200Library._copies}{ext}"
+            while copy in B200Library._loaded_paths:
+                B200Library._copies += 1
+                copy = f"{base}_run{B200Library._copies}{ext}"
+            if os.path.exists(copy):
+                os.unlink(copy)     # a new inode: never write into a file that may be mapped
             shutil.copy2(path, copy)
             path = copy
+        B200Library._loaded_paths.add(path)
         self.path = path
         self.lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
         missing = [s for s in ABI_SYMBOLS if not hasattr(self.lib, s)]

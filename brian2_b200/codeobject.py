@@ -20,7 +20,8 @@ from brian2.devices.device import get_device
 
 from .cuda_generator import CUDACodeGenerator
 
-__all__ = ["B200CodeObject", "B200HostCodeObject", "DEVICE_TEMPLATES", "HOST_TEMPLATES"]
+__all__ = ["B200CodeObject", "B200HostCodeObject", "B200ConnectCodeObject", "B200ShardHostCodeObject",
+           "DEVICE_TEMPLATES", "HOST_TEMPLATES", "RUN_ONCE_DEVICE_TEMPLATES"]
 
 #: templates that run inside the time loop and have a CUDA version
 DEVICE_TEMPLATES = {
@@ -35,6 +36,9 @@ DEVICE_TEMPLATES = {
     "spikegenerator",
     "summed_variable",
 }
+
+#: run-once templates that have a device version (used under "sharded construction" only)
+RUN_ONCE_DEVICE_TEMPLATES = {"synapses_create_generator"}
 
 #: templates that only ever run once, on the host, before/between runs
 HOST_TEMPLATES = {
@@ -99,8 +103,22 @@ class B200HostCodeObject(CPPStandaloneCodeObject):
     generator_class = CPPCodeGenerator
 
 
+class B200ConnectCodeObject(B200CodeObject):
+    """``Synapses.connect`` on the device (templates/synapses_create_generator.cu): a run-once code
+    object whose kernel is compiled into the project's CUDA translation unit."""
+
+
+class B200ShardHostCodeObject(B200HostCodeObject):
+    """Run-once host code object that initialises the variables of a `Synapses` object whose
+    connectivity was created per rank ("sharded construction"): same reference templates, but
+    ``rand()``/``randn()`` are pure functions of the synapse (csrc/b200_synrng.h) instead of
+    draws from the sequential host stream."""
+
+
 codegen_targets.add(B200CodeObject)
 codegen_targets.add(B200HostCodeObject)
+codegen_targets.add(B200ConnectCodeObject)
+codegen_targets.add(B200ShardHostCodeObject)
 
 # ---------------------------------------------------------------------------------------------
 # Function implementations for device code.  Everything that is a plain libm call is inherited
@@ -132,6 +150,38 @@ DEFAULT_FUNCTIONS["randn"].implementations.add_implementation(
     code={"support_code": "", "hashdefine_code": "#define _randn(_i) b200::rng_normal(_rng)"},
     name="_randn",
 )
+
+
+def _synapses_of(owner):
+    """The `Synapses` object behind ``owner`` (itself, or the owner of a `SynapticPathway`)."""
+    return getattr(owner, "synapses", owner)
+
+
+def _generate_synapse_rng_code(func, owner):
+    import zlib
+
+    S = _synapses_of(owner)
+    device = get_device()
+    pre = device.get_array_name(S.variables["_synaptic_pre"], access_data=False)
+    post = device.get_array_name(S.variables["_synaptic_post"], access_data=False)
+    method = {"rand": "uniform", "randn": "normal"}[func]
+    stream = zlib.crc32(f"{owner.name}.{func}".encode())
+    code = f"""
+    static b200::SynapseRng _b200_synrng_{func}({stream}u);
+    inline double _{func}(const int _vectorisation_idx) {{
+        return _b200_synrng_{func}.{method}(_vectorisation_idx, brian::{pre}, brian::{post});
+    }}
+    """
+    return {"support_code": code}
+
+
+for _func in ("rand", "randn"):
+    DEFAULT_FUNCTIONS[_func].implementations.add_dynamic_implementation(
+        B200ShardHostCodeObject,
+        code=(lambda f: (lambda owner: _generate_synapse_rng_code(f, owner)))(_func),
+        namespace=lambda owner: {},
+        name=f"_{_func}",
+    )
 
 
 # ---------------------------------------------------------------------------------------------

@@ -10,8 +10,10 @@
 #include <cuda_runtime_api.h>
 #include <stdint.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -54,6 +56,11 @@ struct RuntimeState {
     double poll_cycles = 0, fence_cycles = 0, polls = 0;   // multi-GPU wait diagnostics
     double upload_seconds = 0.0, download_seconds = 0.0;
     size_t h2d_bytes = 0, d2h_bytes = 0;
+    // synapse creation on the device (b200_connect.cuh)
+    double connect_seconds = 0.0, connect_synapses = 0.0;
+    unsigned long long connect_launches = 0;
+    double prepare_seconds = 0.0;       // host time spent building delay-binned CSRs
+    unsigned long long host_epoch = 1;  // bumped by everything that may change a host array
 };
 
 inline RuntimeState& state() {
@@ -175,6 +182,20 @@ inline void host_allgather(const void* send, void* recv, size_t nbytes) {
     if (s.world <= 1) { memcpy(recv, send, nbytes); return; }
     if (s.allgather(send, recv, nbytes) != 0) throw std::runtime_error("b200: allgather callback failed");
 }
+// Seed of the in-loop Philox streams when the script never called seed(): drawn from the
+// operating system like the reference's generators (objects.cpp:437-440 seeds from
+// std::random_device), so that unseeded runs see different noise; on several GPUs every rank
+// uses rank 0's draw (the shards of one network must agree on the streams).
+inline void ensure_seed() {
+    RuntimeState& s = state();
+    if (s.seeded) return;
+    std::random_device rd;
+    unsigned long long mine = ((unsigned long long)rd() << 32) ^ (unsigned long long)rd();
+    unsigned long long all[kMaxRanks] = {0};
+    host_allgather(&mine, all, sizeof(mine));
+    s.seed = all[0];
+    s.seeded = true;
+}
 inline void host_barrier() {
     if (state().world <= 1) return;
     char one = 1, all[kMaxRanks];
@@ -190,6 +211,7 @@ struct EventSpace {
     int32_t* cnt = nullptr;              // [slots][nseg]  tagged segment counts
     int32_t* compact = nullptr;          // [slots][N+1]   reference layout
     int32_t* seg_start = nullptr;
+    std::vector<int32_t> seg_start_host;
     int slots = 0, N = 0, nb = 0, nseg = 0, id = 0;
     int max_delay = 0;         // over all pathways reading this event space
     int min_delay = 1 << 30;   // ditto (1<<30: no pathway)
@@ -268,6 +290,7 @@ struct EventSpace {
                 start[q * nb + b] = (int32_t)warp_first_host(lo, hi, (int64_t)b * kWarps, (int64_t)nb * kWarps);
         }
         start[nseg] = N;
+        seg_start_host = start;
         dev_free(seg_start);
         seg_start = (int32_t*)dev_alloc((nseg + 1) * sizeof(int32_t));
         B200_CUDA(cudaMemcpy(seg_start, start.data(), (nseg + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -319,6 +342,29 @@ struct EventSpace {
         }
         return v;
     }
+    // Host mirror of the list of step `timestep` in the reference layout (ids ascending in
+    // [0, count), count at [N]), assembled from the segments: works whether or not the device
+    // ever built the compact form (it only does when a delayed / serial pathway reads it).
+    void download_step(int32_t* host, int64_t timestep) const {
+        if (!ids || N <= 0) return;
+        int64_t s = timestep % slots;
+        if (s < 0) s += slots;
+        std::vector<int32_t> c(nseg);
+        std::vector<unsigned long long> w((size_t)N);
+        B200_CUDA(cudaMemcpy(c.data(), cnt + s * (size_t)nseg, nseg * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy(w.data(), ids + s * (size_t)N, (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        int64_t m = (timestep + 1) % 32767;          // == b200::step_tag (b200_runtime.cuh)
+        if (m < 0) m += 32767;
+        const int want = (int)m + 1;
+        int n = 0;
+        for (int j = 0; j < nseg; ++j) {
+            if (timestep < 0 || (c[j] >> 16) != want) continue;
+            const int k = c[j] & 0xffff;
+            for (int q = 0; q < k && n < N; ++q) host[n++] = (int32_t)(unsigned int)w[(size_t)seg_start_host[j] + q];
+        }
+        host[N] = n;
+        state().d2h_bytes += nseg * sizeof(int32_t) + (size_t)N * sizeof(unsigned long long);
+    }
     const int32_t* compact_slot_ptr(int64_t timestep) const {
         int64_t s = timestep % slots;
         if (s < 0) s += slots;
@@ -339,6 +385,7 @@ public:
     size_t n_synapses = 0;
     bool identity = true;
     bool prepared = false;
+    unsigned long long built_epoch = 0;
     std::vector<int> bin_delay;
     // device storage
     int* d_bin_delay = nullptr;
@@ -373,7 +420,16 @@ public:
                  const int* srcs, const int* targets, size_t n_syn, double dt, EventSpace* es_,
                  bool post_is_source, int64_t n_post_parent) {
         runtime_init();
+        // Nothing on the host changed since this CSR was built (the generated main() bumps
+        // host_epoch after every host-side write): keep it, the next run() reuses it as is.
+        if (prepared && built_epoch == state().host_epoch && n_synapses == n_syn && es == es_) {
+            B200_CUDA(cudaMemset(d_tickets, 0, 2 * sizeof(unsigned int)));
+            if (es) es->require(bin_delay.empty() ? 0 : bin_delay.front(), max_delay);
+            return;
+        }
+        const auto _t0 = std::chrono::high_resolution_clock::now();
         release();
+        built_epoch = state().host_epoch;
         Nsource = n_source;
         Ntarget = n_target;
         n_synapses = n_syn;
@@ -473,6 +529,7 @@ public:
         B200_CUDA(cudaMemset(d_tickets, 0, 2 * sizeof(unsigned int)));
         if (es) es->require(bin_delay.empty() ? 0 : bin_delay.front(), max_delay);
         prepared = true;
+        state().prepare_seconds += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - _t0).count();
     }
 
     PathwayDev view() const {

@@ -251,8 +251,9 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int x) {
 // space -- no communication with other CTAs (the reference's loop is serial, threshold.cpp:18-31).
 //   mask   bit k of lane l  <=>  element (slice.lo + 32*k + l) fired
 // Called by ALL threads of ALL CTAs.  On several GPUs every store is repeated into each peer's
-// ring (NVLink P2P); a segment becomes visible to the peers with its count word, which carries
-// the step's tag and is stored last with release semantics at system scope.
+// ring (NVLink P2P).  No ordering between the stores is needed: every word (count and id alike)
+// carries the tag of its time step, and a reader spins on exactly the word it needs until the
+// tag matches (view_build for counts, view_load for ids).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void publish_owned(unsigned long long mask, int niter, const Ctx& c,
                                               const EventSpaceDev& es, int64_t timestep) {
@@ -316,6 +317,7 @@ struct SpikeView {
     const int* pref;        // shared: pref[j - seg_lo] = number of spikes in segments [seg_lo, j)
     int seg_lo, nseg;       // segments covered
     int total;
+    Control* ctrl;          // where a peer time-out is reported
 };
 
 __device__ int* view_storage(long long** tag) {
@@ -354,6 +356,7 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
     v.remote_lo = c.rank * c.gnb;
     v.remote_hi = v.remote_lo + c.gnb;
     v.pref = pref;
+    v.ctrl = ctrl;
     const bool local = local_only && c.world > 1;
     v.seg_lo = local ? c.rank * c.gnb : 0;
     v.nseg = local ? c.gnb : es.nseg;
@@ -428,13 +431,22 @@ __device__ __forceinline__ SpikeView view_build(const EventSpaceDev& es, int64_t
 }
 
 // id stored at position `off` of segment `seg` (absolute segment index); a peer's word may
-// still be in flight: spin until it carries the step's tag
+// still be in flight: spin until it carries the step's tag.  If it never does (~20 s: the peer
+// died), the run is aborted through ctrl->error / the stop flag and the caller gets -1, an id no
+// consumer accepts (pathways range-check the source, the monitors skip negative ids).
 __device__ __forceinline__ int32_t view_load(const SpikeView& v, int seg, int off) {
     const unsigned long long* p = v.ids + v.seg_start[seg] + off;
     unsigned long long w = ld_volatile_u64(p);
     if (seg < v.remote_lo || seg >= v.remote_hi) {
         const long long t0 = clock64();
-        while ((w & 0xffffffff00000000ULL) != v.tag && clock64() - t0 < 40000000000LL) w = ld_volatile_u64(p);
+        while ((w & 0xffffffff00000000ULL) != v.tag) {
+            if (clock64() - t0 > 40000000000LL || ld_volatile_s32(&v.ctrl->error)) {
+                v.ctrl->error = 1;
+                raise_stop(v.ctrl);
+                return -1;
+            }
+            w = ld_volatile_u64(p);
+        }
     }
     return (int32_t)(unsigned int)w;
 }

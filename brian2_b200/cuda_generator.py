@@ -445,6 +445,16 @@ class CUDACodeGenerator(CPPCodeGenerator):
                     f"loop ({', '.join(sorted(sc_write))} in '{self.name}')"
                 )
             ve_read, ve_write, ve_indices, ve_cond = self.arrays_helper(ve_block)
+            if self.template_name == "synapses_create_generator":
+                # the device version of connect() evaluates index arithmetic and rand() only;
+                # conditions that read state variables of the connected groups need the
+                # reference's host path (prefs.devices.b200.construction = 'reference')
+                touched = sorted(ve_read | ve_write | sc_read | ve_indices | sc_indices)
+                if touched:
+                    raise NotImplementedError(
+                        "b200 sharded construction: connect() expressions that read arrays "
+                        f"({', '.join(touched)}) are not supported on the device"
+                    )
             # scalar variables needed by the vector code are read once, in the scalar block
             for varname in set(ve_read):
                 var = self.variables[varname]

@@ -39,8 +39,11 @@ from .capi import B200Library
 from .codeobject import (
     DEVICE_TEMPLATES,
     HOST_TEMPLATES,
+    RUN_ONCE_DEVICE_TEMPLATES,
     B200CodeObject,
+    B200ConnectCodeObject,
     B200HostCodeObject,
+    B200ShardHostCodeObject,
 )
 from .cuda_generator import clock_field, is_eventspace
 
@@ -136,6 +139,33 @@ prefs.register_preferences(
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
+    construction=BrianPreference(
+        default="reference",
+        docs="""
+        How ``Synapses.connect`` and the initialisation of synaptic variables are executed.
+
+        ``'reference'``: the reference's own host C++ (one sequential mt19937 stream): connectivity,
+        delays and weights are bit-identical to ``cpp_standalone`` for the same ``seed()``; on
+        several GPUs every rank builds the whole network and keeps its share.
+
+        ``'sharded'``: ``connect()`` generator expressions run as CUDA kernels (one Philox stream
+        per source row, csrc/b200_connect.cuh) and every rank creates ONLY the synapses whose
+        postsynaptic neuron it owns; ``rand()``/``randn()`` in expressions assigned to synaptic
+        variables are functions of the synapse, not of its position in a stream.  Statistically
+        equivalent to the reference, identical on any number of GPUs, and the way to networks
+        that do not fit one host (10^9 synapses).
+        """,
+        validator=lambda v: v in ("reference", "sharded"),
+    ),
+    gather_synapses_limit=BrianPreference(
+        default=50_000_000,
+        docs="""
+        Several GPUs, sharded construction: after a run the per-rank synapses of a `Synapses`
+        object (indices and every synaptic variable) are gathered on all ranks only if there are
+        at most this many of them in total; larger objects stay distributed (each rank sees the
+        synapses of its own postsynaptic neurons).
+        """,
+    ),
     csr_l2_evict_last=BrianPreference(
         default=False,
         docs="""
@@ -180,6 +210,9 @@ class B200Device(CPPStandaloneDevice):
         self._b200_written_vars = set()
         #: arrays from function namespaces (TimedArray values ...): name -> (ctype, size)
         self._b200_func_arrays = {}
+        #: names of the Synapses objects whose synapses exist per rank only (sharded construction)
+        self._b200_sharded_synapses = set()
+        self._b200_sharded_objects = {}
         self.cu_source_files = []
 
     # ------------------------------------------------------------------------------------------
@@ -203,8 +236,21 @@ class B200Device(CPPStandaloneDevice):
         override_conditional_write=None,
         compiler_kwds=None,
     ):
-        if template_name in HOST_TEMPLATES:
+        sharded = prefs.devices.b200.construction == "sharded"
+        synapses_name = getattr(getattr(owner, "synapses", owner), "name", None)
+        if sharded and template_name in RUN_ONCE_DEVICE_TEMPLATES:
+            codeobj_class = B200ConnectCodeObject
+        elif template_name in HOST_TEMPLATES:
             codeobj_class = B200HostCodeObject
+            if synapses_name in self._b200_sharded_synapses:
+                if template_name.startswith("synapses_create"):
+                    raise NotImplementedError(
+                        f"b200 sharded construction: '{synapses_name}' already has synapses created on "
+                        "the device; connect(i=array, j=array) cannot be mixed with them"
+                    )
+                codeobj_class = B200ShardHostCodeObject
+                compiler_kwds = dict(compiler_kwds or {})
+                compiler_kwds["headers"] = list(compiler_kwds.get("headers", [])) + ['"b200_synrng.h"']
         elif template_name in DEVICE_TEMPLATES:
             codeobj_class = B200CodeObject
         else:
@@ -212,6 +258,15 @@ class B200Device(CPPStandaloneDevice):
                 f"The b200 device has no CUDA template for '{template_name}' code objects yet."
             )
         template_kwds = dict(template_kwds) if template_kwds is not None else {}
+        if codeobj_class is B200ConnectCodeObject:
+            import zlib
+
+            n_calls = sum(1 for info in self._b200_info.values()
+                          if info["template"] == template_name and info["owner"] is owner)
+            template_kwds["b200_stream_id"] = zlib.crc32(f"{owner.name}.connect.{n_calls}".encode())
+            template_kwds["b200_template_name"] = template_name
+            post_parent = getattr(owner.target, "source", owner.target)
+            template_kwds["b200_post_parent_size"] = int(len(post_parent))
         if codeobj_class is B200CodeObject:
             import zlib
 
@@ -258,7 +313,13 @@ class B200Device(CPPStandaloneDevice):
             override_conditional_write=override_conditional_write,
             compiler_kwds=compiler_kwds,
         )
-        if codeobj_class is B200CodeObject:
+        if codeobj_class is B200ConnectCodeObject:
+            self._b200_sharded_synapses.add(owner.name)
+            try:
+                self._b200_sharded_objects[owner.name] = owner.__repr__.__self__
+            except (AttributeError, ReferenceError):
+                pass
+        if codeobj_class in (B200CodeObject, B200ConnectCodeObject):
             try:    # a strong reference: `build()` may be called after the script's objects went
                 owner = owner.__repr__.__self__     # out of scope (build_on_run=False)
             except (AttributeError, ReferenceError):
@@ -620,6 +681,8 @@ class B200Device(CPPStandaloneDevice):
             if not self.is_device_codeobj(codeobj):
                 continue
             code = None
+            if self._b200_info[codeobj.name]["template"] in RUN_ONCE_DEVICE_TEMPLATES:
+                continue    # works on its own scratch buffers and the host mirrors
             if self._b200_info[codeobj.name]["template"] == "synapses_push_spikes":
                 # no device code at all (the spike ring makes the push a no-op): its variables
                 # -- the per-synapse `delay` array above all -- are read by the HOST-side
@@ -790,7 +853,21 @@ class B200Device(CPPStandaloneDevice):
         # reuse the inherited construction of `main_lines`; the template lookup goes through
         # code_object_class() and therefore renders OUR main template
         B200CodeObject.templater.env.globals["profiled_codeobjects"] = list(self.profiled_codeobjects)
-        super().generate_main_source(writer)
+        # Everything that can change a host array between two run() calls bumps the runtime's
+        # "host epoch": a pathway whose inputs are untouched since its CSR was built is not
+        # rebuilt (and re-uploaded) by the `_before_run_*_push_spikes()` of the next run.
+        mutators = {"run_code_object", "set_by_constant", "set_by_array", "set_by_single_value",
+                    "set_array_by_array", "resize_array"}
+        queue = []
+        for func, args in self.main_queue:
+            queue.append((func, args))
+            if func in mutators or (func == "insert_code" and "b200::state()" not in str(args)):
+                queue.append(("insert_code", "b200::state().host_epoch++;"))
+        original, self.main_queue = self.main_queue, queue
+        try:
+            super().generate_main_source(writer)
+        finally:
+            self.main_queue = original
 
     def generate_run_source(self, writer):
         run_tmp = CPPStandaloneCodeObject.templater.run(
@@ -1094,6 +1171,8 @@ class B200Device(CPPStandaloneDevice):
                     if v.name == "rate":
                         parts = comm.allgather_object(local(v))
                         merged[v] = mg.merge_rate(parts, float(owner.clock.dt_), len(owner.source))
+            elif isinstance(owner, Synapses) and owner.name in self._b200_sharded_synapses:
+                pass    # gathered below (every rank holds different synapses)
             elif isinstance(owner, Synapses):
                 post = local(owner.variables["_synaptic_post"])
                 target = owner.target
@@ -1110,6 +1189,35 @@ class B200Device(CPPStandaloneDevice):
                         continue
                     parts = comm.allgather_object(local(v))
                     merged[v] = mg.merge_by_block(parts, len(owner), world)
+        # Synapses created per rank (sharded construction): the global object is the union of the
+        # ranks' synapses in (pre, post) order -- the order a single-GPU run creates them in.
+        limit = int(prefs.devices.b200.gather_synapses_limit)
+        for name in sorted(self._b200_sharded_synapses):
+            S = self._b200_sharded_objects.get(name)
+            if S is None:
+                continue
+            pre_l = np.asarray(local(S.variables["_synaptic_pre"]))
+            sizes = comm.allgather_object(int(len(pre_l)))
+            if sum(sizes) > limit:
+                logger.info(f"'{name}': {sum(sizes)} synapses stay distributed over the ranks "
+                            "(prefs.devices.b200.gather_synapses_limit)")
+                continue
+            post_l = np.asarray(local(S.variables["_synaptic_post"]))
+            order = mg.sharded_synapse_order(comm.allgather_object(pre_l), comm.allgather_object(post_l))
+            seen = set()
+            for var in list(S._registered_variables):
+                if var in seen:
+                    continue
+                seen.add(var)
+                value = merged.get(var)
+                if value is not None and len(value) == len(order):
+                    continue
+                parts = comm.allgather_object(np.asarray(local(var)))
+                merged[var] = np.concatenate(parts)[order]
+            for vname in ("N_incoming", "N_outgoing"):
+                var = S.variables[vname]
+                merged[var] = np.sum(np.stack(comm.allgather_object(np.asarray(local(var)))), axis=0).astype(var.dtype)
+            merged[S.variables["N"]] = np.array([len(order)], dtype=S.variables["N"].dtype)
         for v, value in merged.items():
             self.array_cache[v] = value
             if isinstance(v, DynamicArrayVariable) and getattr(v, "ndim", 1) == 1:

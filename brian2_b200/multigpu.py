@@ -5,7 +5,8 @@ group -- their state, thresholding, reset and monitors -- and every synapse whos
 neuron lies in the block, so all synaptic effects are local writes.  The only data that crosses
 GPUs inside the step loop are the spike lists: each rank stores its segment of every step's list
 directly into the peers' spike rings over NVLink (CUDA-IPC mapped peer memory, see
-``csrc/b200_runtime.cuh``: ``publish_owned`` / ``publish_done`` / ``wait_peers``).
+``csrc/b200_runtime.cuh``: ``publish_owned`` stores tagged words, ``view_build`` / ``view_load``
+spin on the tag of the word they need -- flag and data travel together).
 
 This module holds what happens on the host, outside the loop:
 
@@ -138,6 +139,16 @@ def merge_rate(counts, dt, n_source):
     device on several GPUs); the reference's formula is applied once to the exact total."""
     total = np.sum(np.stack(counts), axis=0)
     return 1.0 * total / dt / n_source
+
+
+def sharded_synapse_order(pre_parts, post_parts):
+    """Sharded construction: every rank created the synapses of its own postsynaptic neurons,
+    each rank's list in (pre, post) order.  Returns the permutation that puts the concatenation
+    of the ranks' lists into the order a single-GPU run creates the same synapses in:
+    (pre ascending, post ascending), equal pairs (multiple synapses) in creation order."""
+    pre_all = np.concatenate([np.asarray(p) for p in pre_parts])
+    post_all = np.concatenate([np.asarray(p) for p in post_parts])
+    return np.lexsort((post_all, pre_all))      # lexsort is stable
 
 
 def merge_value(kind, parts, **kw):

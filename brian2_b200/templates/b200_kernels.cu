@@ -4,6 +4,7 @@
 #include "b200_objects.h"
 #include "b200_runtime.cuh"
 #include "b200_functions.cuh"
+#include "b200_connect.cuh"
 #include "network.h"
 #include "b200_plans.h"
 #include <cooperative_groups.h>

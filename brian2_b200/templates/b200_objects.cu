@@ -137,6 +137,7 @@ void _b200_upload()
         memset(&_A_host, 0, sizeof(_A_host));
         _b200_first_upload = false;
     }
+    b200::ensure_seed();
     _A_host._seed = st.seed;
     _A_host._ctrl = st.control;
     _A_host._stop_request = st.stop_request_dev;
@@ -339,8 +340,7 @@ void _b200_download()
     {% if a.eventspace %}
     {
         // host mirror of an event space = the list of the last executed step
-        const long long _last = _b200_clocks_now().{{a.clock}}.timestep - 1 - _b200_es{{a.name}}.lag();
-        b200::download_array(brian::{{a.name}}, _b200_es{{a.name}}.compact_slot_ptr(_last), {{a.size}});
+        _b200_es{{a.name}}.download_step(brian::{{a.name}}, _b200_clocks_now().{{a.clock}}.timestep - 1);
     }
     {% elif a.kind == 'static' %}
     b200::download_array(brian::{{a.name}}, _A_host.{{a.name}}, {{a.size}});

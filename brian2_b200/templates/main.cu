@@ -51,6 +51,7 @@ static void _b200_crash_handler(int sig)
 
 void set_from_command_line(const std::vector<std::string> args)
 {
+    if (!args.empty()) b200::state().host_epoch++;   // host arrays may change: CSRs are rebuilt
     for (const auto& arg : args) {
         size_t equal_sign = arg.find("=");
         auto name = arg.substr(0, equal_sign);
@@ -160,6 +161,10 @@ double b200_get_counter(const char* key)
     if (k == "poll_cycles") return st.poll_cycles;
     if (k == "fence_cycles") return st.fence_cycles;
     if (k == "polls") return st.polls;
+    if (k == "connect_seconds") return st.connect_seconds;
+    if (k == "connect_synapses") return st.connect_synapses;
+    if (k == "connect_launches") return (double)st.connect_launches;
+    if (k == "prepare_seconds") return st.prepare_seconds;
     if (k == "grid") return st.initialised ? (double)_b200_grid_size() : 0.0;
     if (k == "runs") return (double)Network::_b200_run_log.size();
     if (k.compare(0, 5, "phase") == 0) {   // "phase<i>": cycles CTA 0 spent in phase i (profile_phases)
@@ -182,6 +187,7 @@ double b200_get_counter(const char* key)
                 if (f == "t0_unix") return r.t0_unix;
                 if (f == "upload_seconds") return r.upload_seconds;
                 if (f == "download_seconds") return r.download_seconds;
+                if (f == "prepare_seconds") return r.prepare_seconds;
                 if (f == "events") return r.events;
                 if (f == "steps") return (double)r.steps;
                 if (f == "persistent") return (double)r.persistent;

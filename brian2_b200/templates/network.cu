@@ -214,6 +214,9 @@ void Network::run(const double duration, void (*report_func)(const double, const
         rec.events = (double)(_b200_events_delivered() - _events_before);
         rec.upload_seconds = b200::state().upload_seconds - _upload_before;
         rec.download_seconds = b200::state().download_seconds - _download_before;
+        static double _prepare_seen = 0.0;
+        rec.prepare_seconds = b200::state().prepare_seconds - _prepare_seen;
+        _prepare_seen = b200::state().prepare_seconds;
         rec.persistent = persistent ? 1 : 0;
         Network::_b200_run_log.push_back(rec);
     }
@@ -245,6 +248,7 @@ struct B200RunRecord {
     double wall_seconds;       // host clock around the same region
     double t0_unix;            // host time (seconds since the epoch) when the loop started
     double upload_seconds, download_seconds;
+    double prepare_seconds;    // host time spent (re)building pathway CSRs since the previous run
     double events;             // synaptic events delivered during this run
     long long steps;
     int persistent;

@@ -12,6 +12,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_visible():
+    """True iff the CUDA driver reports at least one device (no torch import needed)."""
+    import ctypes
+
+    for name in ("libcuda.so.1", "libcuda.so"):
+        try:
+            cuda = ctypes.CDLL(name)
+        except OSError:
+            continue
+        count = ctypes.c_int(0)
+        if cuda.cuInit(0) == 0 and cuda.cuDeviceGetCount(ctypes.byref(count)) == 0:
+            return count.value > 0
+        return False
+    return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not failed) on a box that has nvcc but no GPU."""
+    if _cuda_device_visible():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def brian():
     """The Brian2 front-end (reference install under oracle/_ref) with the b200 device registered."""

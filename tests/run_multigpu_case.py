@@ -28,6 +28,9 @@ def main(cases):
     from golden.make_golden import CASES
 
     failures = []
+    if cases and cases[0] == "--sharded":
+        failures = sharded(b, models, CASES, cases[1:], rank, dist)
+        cases = []
     for case in cases:
         model, kwds = CASES[case]
         d = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"mgpu_{case}_r{rank}")
@@ -51,6 +54,44 @@ def main(cases):
         print("MULTIGPU", "FAIL" if failures else "OK", failures, flush=True)
     dist.destroy_process_group()
     sys.exit(1 if failures else 0)
+
+
+def sharded(b, models, CASES, cases, rank, dist):
+    """Sharded construction: N ranks against ONE rank (rank 0 re-runs the script on its own)."""
+    failures = []
+    for case in cases:
+        model, kwds = CASES[case]
+        runs = {}
+        for mode in ("ranks", "single"):
+            if mode == "single" and rank != 0:
+                continue
+            d = os.path.join(ROOT, "brian2_b200", "_prebuilt", f"mgpu_sharded_{mode}_{case}_r{rank}")
+            objs, res = models.run_model(
+                b, model, "b200", d,
+                prefs_update={"devices.b200.construction": "sharded",
+                              "devices.b200.multi_gpu": mode == "ranks"}, **kwds)
+            for key, obj in objs.items():
+                if isinstance(obj, b.Synapses):
+                    res[f"{key}_i"] = np.asarray(obj.i[:])
+                    res[f"{key}_j"] = np.asarray(obj.j[:])
+                    if "delay" in obj.variables and len(np.atleast_1d(obj.delay_[:])) == len(obj):
+                        res[f"{key}_delay"] = np.asarray(obj.delay_[:])
+            runs[mode] = res
+            print(f"[rank {rank}] {case} ({mode}): {len(res.get('spikes_i', []))} spikes, "
+                  f"local events {int(b.device.counter('events'))}", flush=True)
+        b.prefs["devices.b200.construction"] = "reference"
+        b.prefs["devices.b200.multi_gpu"] = True
+        if rank == 0:
+            for key, ref in runs["single"].items():
+                got = runs["ranks"][key]
+                if key == "last_run_time":
+                    continue
+                if ref.shape != got.shape:
+                    failures.append(f"{case}:{key} shape {got.shape} != {ref.shape}")
+                elif not np.array_equal(ref, got):
+                    failures.append(f"{case}:{key} differs ({int(np.sum(ref != got))} of {ref.size})")
+        dist.barrier()
+    return failures
 
 
 if __name__ == "__main__":

@@ -92,6 +92,22 @@ def _worker(rank, world, port, tmpdir):
     trace_local = np.where(own_i[None, :] == rank, trace_true, np.nan)
     trace = mg.merge_state_columns(comm.allgather_object(trace_local), indices, N, world)
     assert np.array_equal(trace, trace_true)
+    # sharded construction: every rank holds the synapses of ITS postsynaptic neurons, in
+    # (pre, post) order; the merged object has the single-GPU order
+    pre_g = np.sort(rng.randint(0, N, S)).astype(np.int32)
+    post_g = rng.randint(0, N, S).astype(np.int32)
+    order_g = np.lexsort((post_g, pre_g))
+    pre_g, post_g = pre_g[order_g], post_g[order_g]
+    delay_g = rng.rand(S)
+    mine = mg.owner_of(post_g, N, world) == rank
+    parts = comm.allgather_object({"pre": pre_g[mine], "post": post_g[mine], "delay": delay_g[mine]})
+    order = mg.sharded_synapse_order([p["pre"] for p in parts], [p["post"] for p in parts])
+    assert np.array_equal(np.concatenate([p["pre"] for p in parts])[order], pre_g)
+    assert np.array_equal(np.concatenate([p["post"] for p in parts])[order], post_g)
+    pairs = pre_g.astype(np.int64) * N + post_g
+    unique = np.concatenate([[True], pairs[1:] != pairs[:-1]]) & np.concatenate([pairs[1:] != pairs[:-1], [True]])
+    merged_delay = np.concatenate([p["delay"] for p in parts])[order]
+    assert np.array_equal(merged_delay[unique], delay_g[unique])
     with open(os.path.join(tmpdir, f"ok{rank}"), "w") as f:
         f.write("ok")
     dist.destroy_process_group()
