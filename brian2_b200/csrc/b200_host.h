@@ -61,6 +61,9 @@ struct RuntimeState {
     unsigned long long connect_launches = 0;
     double prepare_seconds = 0.0;       // host time spent building delay-binned CSRs
     unsigned long long host_epoch = 1;  // bumped by everything that may change a host array
+    // every pathway of the project delivers at least one step after the spike (decided at
+    // upload): the step kernels of the 'd1' variant run (no end-of-step barrier, see device.py)
+    bool all_delayed = false;
 };
 
 inline RuntimeState& state() {
@@ -226,8 +229,12 @@ struct EventSpace {
     }
     // On several GPUs a step is compacted only when a consumer can first need it (min delay - 1
     // steps later), so that the wait for the peers' segments never stalls the step loop.
+    // 'd1' variant (all delays >= 1 step): the list of the previous step is read from the
+    // segments, compacted lists are first needed two steps after the spike.
     int lag() const {
-        if (state().world <= 1 || min_delay == (1 << 30)) return 0;
+        if (min_delay == (1 << 30)) return 0;
+        if (state().all_delayed) return std::max(0, min_delay - 2);
+        if (state().world <= 1) return 0;
         return std::max(0, min_delay - 1);
     }
     int required_slots() const { return 2 * (max_delay + 1) + 2; }
@@ -332,7 +339,7 @@ struct EventSpace {
         v.ids = ids; v.cnt = cnt; v.compact = compact; v.seg_start = seg_start;
         v.slots = slots; v.N = N; v.nseg = nseg; v.lag = lag(); v.id = id;
         // the reference layout is only built when somebody reads it (delayed or serial pathways)
-        v.need_compact = (compact_always || max_delay > 0) ? 1 : 0;
+        v.need_compact = (compact_always || max_delay > (state().all_delayed ? 1 : 0)) ? 1 : 0;
         int64_t lo, hi;
         rank_range_host(N, st.rank, st.world, lo, hi);
         v.rank_lo = (int)lo; v.rank_hi = (int)hi;
@@ -386,6 +393,7 @@ public:
     bool identity = true;
     bool prepared = false;
     unsigned long long built_epoch = 0;
+    double built_dt = 0.0;
     std::vector<int> bin_delay;
     // device storage
     int* d_bin_delay = nullptr;
@@ -394,6 +402,8 @@ public:
     int* d_csr_target = nullptr;
     unsigned long long* d_events = nullptr;
     unsigned int* d_tickets = nullptr;
+    int* d_hits = nullptr;
+    int hits_n = 0;
     EventSpace* es = nullptr;
     size_t n_owned = 0;            // synapses stored on this rank (post neuron owned)
 
@@ -422,7 +432,7 @@ public:
         runtime_init();
         // Nothing on the host changed since this CSR was built (the generated main() bumps
         // host_epoch after every host-side write): keep it, the next run() reuses it as is.
-        if (prepared && built_epoch == state().host_epoch && n_synapses == n_syn && es == es_) {
+        if (prepared && built_epoch == state().host_epoch && n_synapses == n_syn && es == es_ && built_dt == dt) {
             B200_CUDA(cudaMemset(d_tickets, 0, 2 * sizeof(unsigned int)));
             if (es) es->require(bin_delay.empty() ? 0 : bin_delay.front(), max_delay);
             return;
@@ -430,6 +440,7 @@ public:
         const auto _t0 = std::chrono::high_resolution_clock::now();
         release();
         built_epoch = state().host_epoch;
+        built_dt = dt;
         Nsource = n_source;
         Ntarget = n_target;
         n_synapses = n_syn;
@@ -532,13 +543,25 @@ public:
         state().prepare_seconds += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - _t0).count();
     }
 
+    // counted pathways: two zeroed counter arrays (by step parity) over the target group
+    void ensure_hits(int n) {
+        if (n <= 0 || (d_hits && hits_n == n)) return;
+        dev_free(d_hits);
+        hits_n = n;
+        d_hits = (int*)dev_alloc(2 * (size_t)n * sizeof(int));
+        B200_CUDA(cudaMemset(d_hits, 0, 2 * (size_t)n * sizeof(int)));
+    }
+
     PathwayDev view() const {
         PathwayDev v;
         v.nsrc = spikes_stop - spikes_start;
         v.src_start = spikes_start;
         v.nbins = nbins;
         v.identity = identity ? 1 : 0;
-        v.has_delay0 = (!bin_delay.empty() && bin_delay.front() == 0) ? 1 : 0;
+        const int seg = state().all_delayed ? 1 : 0;
+        v.seg_delay = (!bin_delay.empty() && bin_delay.front() == seg) ? seg : -1;
+        v.hits = d_hits;
+        v.hits_n = hits_n;
         v.bin_delay = d_bin_delay;
         v.bin_maxlen = d_bin_delay + nbins;
         v.rowptr = d_rowptr;

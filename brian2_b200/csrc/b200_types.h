@@ -66,7 +66,10 @@ struct PathwayDev {
     int src_start;            // first source id in the parent group (spikequeue.h:97,162)
     int nbins;                // distinct integer delays
     int identity;             // 1: csr slot k == synapse index k (no indirection needed)
-    int has_delay0;           // 1: the first bin has delay 0 (the current step's list is needed)
+    int seg_delay;            // delay (0 or 1 step) whose spike list is read straight from the
+                              // thresholder's segments, -1: none (older lists: compacted form)
+    int* hits;                // counted pathways: [2][hits_n] events per target, by step parity
+    int hits_n;
     const int* bin_delay;     // [nbins] delay in steps, ascending
     const int* bin_maxlen;    // [nbins] length of the longest row of the bin
     const int* rowptr;        // [nbins*(nsrc+1)+1] slot offsets

@@ -419,6 +419,52 @@ class CUDACodeGenerator(CPPCodeGenerator):
         return lines
 
     # ------------------------------------------------------------------------------------------
+    # "counted" pathways: synaptic code whose effect is a function of the TARGET element only
+    # ------------------------------------------------------------------------------------------
+    def _countable(self, statements, read, write, indices):
+        """Description of a synaptic effect that touches nothing but data of the element at the
+        non-source end of the synapse (`v_post += J`, `ge_post += we`, `v_post += c*(E - v_post)`,
+        with or without `(unless refractory)`): no synaptic variable, no source-side variable, no
+        random numbers.  Such code gives the same result whether it runs once per event or --
+        what the device does -- the events are COUNTED per target (integer reductions) and the
+        owner of the target applies the statements that many times, in the reference's order
+        (synapses.cpp:20-49 walks the events of one pathway one after the other).  Returns
+        ``None`` if the code does not qualify, else ``{"index", "size", "read", "write"}``."""
+        pathway = getattr(self.device, "_b200_current_template_kwds", {}).get("pathway")
+        prepost = getattr(pathway, "prepost", None)
+        if prepost not in ("pre", "post") or not statements or not write:
+            return None
+        tgt_index = "_postsynaptic_idx" if prepost == "pre" else "_presynaptic_idx"
+        for var in self.variables.values():
+            if isinstance(var, Function) and not getattr(var, "stateless", True):
+                idents = set()
+                for stmt in statements:
+                    idents |= get_identifiers(str(stmt.expr))
+                if any(self.variables.get(i) is var for i in idents):
+                    return None
+        arrays = set(read) | set(write)
+        sizes, owners = set(), set()
+        for name in arrays:
+            var = self.variables[name]
+            if self.variable_indices[name] != tgt_index or getattr(var, "dynamic", False):
+                return None
+            sizes.add(int(var.size))
+            owners.add(getattr(var.owner, "name", None))
+        if set(indices) - {tgt_index} or len(sizes) != 1 or len(owners) != 1:
+            return None
+        return {"index": tgt_index, "size": sizes.pop(), "read": sorted(read), "write": sorted(write)}
+
+    def _counted_apply_lines(self, statements, read, write, indices, cond_write, info):
+        """(loads, body, stores) of the apply loop: plain sequential code on local copies."""
+        loads = self.translate_to_read_arrays(read, write, indices)
+        loads = [re.sub(r"^const int32_t (_presynaptic_idx|_postsynaptic_idx) = \w+\[_idx\];$",
+                        r"const int32_t \1 = _b200_tgt_idx;", line) for line in loads]
+        loads += self.translate_to_declarations(read, write, indices)
+        body = self.translate_to_statements(statements, cond_write)
+        stores = self.translate_to_write_arrays(write)
+        return loads, body, stores
+
+    # ------------------------------------------------------------------------------------------
     def translate_statement_sequence(self, sc_statements, ve_statements):
         assert set(sc_statements.keys()) == set(ve_statements.keys())
         kwds = self.determine_keywords()
@@ -474,6 +520,33 @@ class CUDACodeGenerator(CPPCodeGenerator):
             )
 
             # ---- vector block
+            counted = None
+            if self._is_synaptic_effect() and len(ve_block) and prefs["devices.b200.counted_pathways"] != "never":
+                counted = self._countable(ve_block, ve_read, ve_write, ve_indices)
+                if counted is not None and prefs["devices.b200.counted_pathways"] == "auto":
+                    # pure `x_post += constant` scatters are served as well by fp atomics (one phase
+                    # less); counting pays as soon as the code reads target-side data
+                    # (`(unless refractory)` conditions, `v_post += c*(E - v_post)`)
+                    if not (set(ve_read) - set(ve_write)) and all(
+                            s.inplace and s.op in ("+=", "-=") and not (get_identifiers(str(s.expr)) & set(ve_write))
+                            for s in ve_block):
+                        counted = None
+            if counted is not None:
+                loads, body, stores = self._counted_apply_lines(ve_block, ve_read, ve_write, ve_indices, ve_cond, counted)
+                kwds["b200_apply_loads"] = stripped_deindented_lines("\n".join(loads))
+                kwds["b200_apply_body"] = stripped_deindented_lines("\n".join(body))
+                kwds["b200_apply_stores"] = stripped_deindented_lines("\n".join(stores))
+                ve_code[block_name] = ["atomicAdd(_b200_hits + _b200_tgt_idx, 1);"]
+                self._b200_unroll, self._b200_preloads = 4, []
+                name_of = lambda n: self.device.get_array_name(self.variables[n], access_data=False)
+                access["counted"] = {"size": counted["size"],
+                                     "read": sorted(name_of(n) for n in counted["read"]),
+                                     "write": sorted(name_of(n) for n in counted["write"])}
+                for name in sc_read | sc_indices:
+                    var = self.variables.get(name)
+                    if isinstance(var, ArrayVariable):
+                        access["read"].add(self.device.get_array_name(var, access_data=False))
+                continue
             if self._is_synaptic_effect() and len(ve_block):
                 try:
                     if self.has_repeated_indices(ve_block):
@@ -508,6 +581,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
             scal_host, scal_members = scal_host[None], scal_members[None]
         kwds["b200_scalar_host"] = scal_host
         kwds["b200_scalar_members"] = scal_members
+        kwds["b200_counted"] = access.get("counted")
         kwds["b200_serial"] = serial
         kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)
         kwds["b200_gather_unroll"] = 2 if kwds["b200_unroll"] > 1 else 1

@@ -139,6 +139,30 @@ prefs.register_preferences(
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
+    elide_end_barrier=BrianPreference(
+        default=True,
+        docs="""
+        When every synaptic pathway of the project delivers at least one time step after the
+        spike, run the variant of the persistent kernel whose deliveries overlap the state
+        update of the same step and that needs no grid barrier at the end of a step.
+        """,
+    ),
+    counted_pathways=BrianPreference(
+        default="always",
+        docs="""
+        Synaptic code that only touches data of the element at the non-source end of a synapse
+        (``v_post += J``, with or without ``(unless refractory)``; ``v_post += c*(E - v_post)``)
+        can be executed by COUNTING the events per target (integer reductions, no floating-point
+        atomics, no gather of target-side state per event) and letting the owner of every target
+        apply the statements that many times in the reference's order: bit-identical to the
+        sequential reference whatever the constants, several pathways may deliver into one
+        variable inside the same phase of a step, and dense rows are accumulated in shared memory.
+        ``'always'``: whenever the code qualifies; ``'auto'``: only when the code reads
+        target-side data (plain ``x_post += constant`` stays a floating-point reduction);
+        ``'never'``.
+        """,
+        validator=lambda v: v in ("always", "auto", "never"),
+    ),
     construction=BrianPreference(
         default="reference",
         docs="""
@@ -422,6 +446,15 @@ class B200Device(CPPStandaloneDevice):
                     return True
             return False
 
+        # counted pathways: the apply pass runs right after the delivery (stepwise mode: its own
+        # launch; the persistent kernel places it through _plan_barriers)
+        for i in range(len(run_lines) - 1, -1, -1):
+            m = _re.match(rf"\s*{_re.escape(net.name)}\.add\(&(\w+), _run_(\w+)\);", run_lines[i])
+            if m and m.group(2) in self.code_objects and \
+                    self._b200_access.get(m.group(2), {}).get("counted"):
+                run_lines.insert(i + 1, f"{net.name}.add(&{m.group(1)}, _run_{m.group(2)}_apply);")
+                if i <= last_add:
+                    last_add += 1
         extra_lines = []
         for clock, es_name in compactions:
             item = (clock, ("compact", es_name, clock.name))
@@ -509,6 +542,11 @@ class B200Device(CPPStandaloneDevice):
         if template in ("spikemonitor", "statemonitor", "ratemonitor"):
             for var in self._monitor_buffers(codeobj):
                 shared_w.add(name_of(var))
+        if template == "synapses" and acc.get("counted"):
+            # the delivery only counts events; the target arrays are touched by the apply pass,
+            # element-private (listed here so that they reach the device and come back)
+            priv_r |= set(acc["counted"]["read"])
+            priv_w |= set(acc["counted"]["write"])
         # scalars that never change inside a run cannot create a dependency
         drop = set()
         for var in codeobj.variables.values():
@@ -516,40 +554,107 @@ class B200Device(CPPStandaloneDevice):
                 drop.add(name_of(var))
         return priv_r - drop, priv_w - drop, shared_r - drop, shared_w - drop
 
-    def _plan_barriers(self, entries):
-        """Greedy phase construction: a grid barrier is placed in front of a code object iff it
-        conflicts (RAW/WAR/WAW on an array, unless both accesses are element-private with the
-        same owned partition) with something executed since the previous barrier."""
-        items = []
-        ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
-        ph_thresholders = []   # event spaces written since the last barrier (multi-GPU publish)
+    # Resources of the barrier analysis are (name, lo, hi, private): `name` an array (or one of the
+    # per-step structures below), [lo, hi] the range of TIME STEPS (relative to the current one)
+    # whose instance of the structure is touched -- ordinary arrays exist once: (-inf, +inf) --,
+    # `private` = every element is touched only by the CTA that owns it in the common partition.
+    #   "<es>"            per-CTA segments of a step's spike list (ring of past steps)
+    #   "<es>#own"        a CTA's own segment (thresholder -> resetter, same CTA)
+    #   "<es>__compact"   the compacted (reference-layout) list of a step
+    #   "hits:<pathway>"  per-target event counters of a counted pathway (double buffered)
+    _ALWAYS = (float("-inf"), float("inf"))
 
-        def add(name, kind, pr, pw, sr, sw, extra=None, owned=False):
-            nonlocal ph_pr, ph_pw, ph_sr, ph_sw, ph_thresholders
-            conflict = bool(
-                (sw | pw) & (ph_sr | ph_sw)      # I write what somebody read/wrote (shared)
-                or sw & (ph_pr | ph_pw)           # shared write vs private access
-                or (sr | pr) & ph_sw              # I read what somebody wrote (shared)
-                or sr & ph_pw                     # shared read of a privately written array
-            )
-            item = {"name": name, "kind": kind, "barrier": conflict and len(items) > 0, "publish": [],
-                    "owned": owned, "share": None}
-            if conflict:
-                item["publish"] = list(ph_thresholders)
-                ph_pr, ph_pw, ph_sr, ph_sw = set(), set(), set(), set()
-                ph_thresholders = []
+    def _item_resources(self, codeobj, variant):
+        """(reads, writes) of one in-loop code object as lists of resources (see above).
+        `variant`: 'd0' -- a pathway may deliver in the step the spike was emitted in (reads the
+        current step's segments, older steps from their compacted lists); 'd1' -- every delay is
+        at least one step (reads the previous step's segments and compacted lists at least two
+        steps old): what allows a step without an end-of-step barrier."""
+        info = self._b200_info[codeobj.name]
+        template, kw = info["template"], info["template_kwds"]
+        acc = self._b200_access.get(codeobj.name, {})
+        pr, pw, sr, sw = self._codeobj_access(codeobj)
+        R = [(n, *self._ALWAYS, True) for n in pr] + [(n, *self._ALWAYS, False) for n in sr]
+        W = [(n, *self._ALWAYS, True) for n in pw] + [(n, *self._ALWAYS, False) for n in sw]
+        name_of = lambda var: self.get_array_name(var, access_data=False)
+        es = kw.get("eventspace_variable")
+        if template == "synapses":
+            es = kw["pathway"].source.variables[kw["pathway"].eventspace_name]
+        elif template == "ratemonitor":
+            es = codeobj.variables["_spikespace"]
+        E = name_of(es) if es is not None else None
+        # the event-space entries of _codeobj_access are replaced by step-resolved ones
+        R = [r for r in R if r[0] not in (E, f"{E}__compact")]
+        W = [w for w in W if w[0] != E]
+        if template in SPIKE_SOURCE_TEMPLATES:
+            W += [(E, 0, 0, False), (f"{E}#own", 0, 0, True)]
+        elif template == "reset":
+            R += [(f"{E}#own", 0, 0, True)]
+        elif template in ("spikemonitor", "ratemonitor"):
+            R += [(E, 0, 0, False)]
+        elif template == "synapses":
+            if acc.get("serial"):
+                R += [(f"{E}__compact", float("-inf"), 0, False)]
+            elif variant == "d1":
+                R += [(E, -1, -1, False), (f"{E}__compact", float("-inf"), -2, False)]
+            else:
+                R += [(E, 0, 0, False), (f"{E}__compact", float("-inf"), -1, False)]
+            if acc.get("counted"):
+                # the delivery itself only counts; the target arrays belong to the apply item
+                mine = set(acc["counted"]["read"]) | set(acc["counted"]["write"])
+                R = [r for r in R if r[0] not in mine]
+                W = [w for w in W if w[0] not in mine] + [(f"hits:{kw['pathway'].name}", 0, 0, False)]
+        return R, W
+
+    @staticmethod
+    def _resource_conflict(first, second, shift=0):
+        """Dependency between an earlier item `first` and a later item `second` (= (R, W)); the
+        later one's step ranges are moved by `shift` steps (1: it belongs to the next time step).
+        Returns 'hard' (different CTAs may touch the same data: a grid barrier must separate
+        them), 'soft' (element-private on both sides: program order inside the owning CTA is
+        enough) or None."""
+        R1, W1 = first
+        R2, W2 = second
+        found = None
+        for a_list, b_list in ((W1, R2 + W2), (R1, W2)):
+            for (na, la, ha, pa) in a_list:
+                for (nb, lb, hb, pb) in b_list:
+                    if na != nb or ha < lb + shift or hb + shift < la:
+                        continue
+                    if pa and pb:
+                        found = found or "soft"
+                    else:
+                        return "hard"
+        return found
+
+    def _plan_barriers(self, entries, variant="d0"):
+        """Phases of one time step.  Every item goes into the earliest phase its dependencies
+        allow: phase(i) = max(phase(j) + 1 over earlier items j it shares data with across CTAs,
+        phase(j) over earlier items it only shares element-private data with); inside a phase
+        the schedule order is kept.  Items of one phase are mutually independent (or
+        element-private), so a grid barrier is only needed between phases -- and at the end of
+        the step only if an item of the first phase of the NEXT step depends on an item of the
+        last phase of this one.  Returns (items, end_barrier)."""
+        items = []
+
+        def add(name, kind, res, owned, extra=None):
+            item = {"name": name, "kind": kind, "res": res, "owned": owned, "share": None,
+                    "barrier": False, "phase": 0, "order": len(items)}
             if extra:
                 item.update(extra)
+            for other in items:
+                dep = self._resource_conflict(other["res"], res)
+                if dep == "hard":
+                    item["phase"] = max(item["phase"], other["phase"] + 1)
+                elif dep == "soft":
+                    item["phase"] = max(item["phase"], other["phase"])
             items.append(item)
-            ph_pr |= pr
-            ph_pw |= pw
-            ph_sr |= sr
-            ph_sw |= sw
 
         for clock, codeobj in entries:
             if isinstance(codeobj, tuple):   # ("compact", event space array name, clock name)
                 _, es_name, clk = codeobj
-                add(f"compact{es_name}", "compact", set(), set(), {es_name}, {es_name + "__compact"},
+                add(f"compact{es_name}", "compact",
+                    ([(es_name, 0, 0, False)], [(es_name + "__compact", 0, 0, False)]), False,
                     {"es": es_name, "clock": clk})
                 continue
             if not self.is_device_codeobj(codeobj):
@@ -559,36 +664,50 @@ class B200Device(CPPStandaloneDevice):
             info = self._b200_info[codeobj.name]
             if info["template"] == "synapses_push_spikes":
                 continue
-            pr, pw, sr, sw = self._codeobj_access(codeobj)
-            add(codeobj.name, "codeobj", pr, pw, sr, sw, owned=self._is_owned_type(codeobj),
-                extra={"weight": 24 if info["template"] == "synapses" else 1})
-            if info["template"] in SPIKE_SOURCE_TEMPLATES:
-                es = info["template_kwds"]["eventspace_variable"]
-                ph_thresholders.append(
-                    {"es": self.get_array_name(es, access_data=False), "clock": es.owner.clock.name}
-                )
-        # event spaces still unpublished at the end of the step go out with the end-of-step barrier
-        self._b200_tail_publish = list(ph_thresholders)
+            res = self._item_resources(codeobj, variant)
+            add(codeobj.name, "codeobj", res, self._is_owned_type(codeobj),
+                {"weight": 24 if info["template"] == "synapses" else 1, "variant": variant})
+            counted = self._b200_access.get(codeobj.name, {}).get("counted")
+            if info["template"] == "synapses" and counted:
+                # the owners of the targets apply the counted events (element-private)
+                hits = f"hits:{info['template_kwds']['pathway'].name}"
+                R = [(n, *self._ALWAYS, True) for n in counted["read"]] + [(hits, 0, 0, False)]
+                W = [(n, *self._ALWAYS, True) for n in counted["write"]]
+                add(codeobj.name, "apply", (R, W), True, {"variant": variant})
+        items.sort(key=lambda it: (it["phase"], it["order"]))
+        last = -1
+        for it in items:
+            it["barrier"] = it["phase"] != last and last >= 0
+            last = it["phase"]
+        # end-of-step barrier: first phase of the next step against the last phase of this one
+        n_phases = (items[-1]["phase"] + 1) if items else 0
+        end_barrier = n_phases <= 1
+        if not end_barrier:
+            first = [it for it in items if it["phase"] == 0]
+            later = [it for it in items if it["phase"] > 0]
+            for b_item in first:
+                for a_item in later:
+                    if self._resource_conflict(a_item["res"], b_item["res"], shift=1) == "hard":
+                        end_barrier = True
+            # (items of phase 0 against each other one step apart: always separated by the
+            # barriers in between, of which there is at least one)
         # Side-by-side execution: the code objects of one phase are mutually independent (that is
         # what "no barrier between them" means), and the ones that are not tied to the element
         # partition are short latency chains -- each gets its own share of the CTAs instead of
         # all CTAs walking through them one after the other.
         if prefs.devices.b200.split_phases:
-            phase = []
-            for item in items + [None]:
-                if item is None or item["barrier"]:
-                    free = [it for it in phase if not it["owned"]]
-                    if len(free) > 1:
-                        total = sum(it.get("weight", 1) for it in free)
-                        acc = 0
-                        for it in free:
-                            w = it.get("weight", 1)
-                            it["share"] = (acc, acc + w, total)
-                            acc += w
-                    phase = []
-                if item is not None:
-                    phase.append(item)
-        return items
+            for ph in range(n_phases):
+                free = [it for it in items if it["phase"] == ph and not it["owned"]]
+                if len(free) > 1:
+                    total = sum(it.get("weight", 1) for it in free)
+                    acc = 0
+                    for it in free:
+                        w = it.get("weight", 1)
+                        it["share"] = (acc, acc + w, total)
+                        acc += w
+        for it in items:
+            del it["res"]
+        return items, end_barrier
 
     def _is_owned_type(self, codeobj):
         info = self._b200_info[codeobj.name]
@@ -801,12 +920,21 @@ class B200Device(CPPStandaloneDevice):
         out = []
         for S in sorted(synapses, key=lambda s: s.name):
             for path in sorted(S._pathways, key=lambda p: p.name):
+                hits_n = 0
+                for codeobj in self.code_objects.values():
+                    info = self._b200_info.get(codeobj.name)
+                    if info is not None and info["template"] == "synapses" \
+                            and info["template_kwds"]["pathway"].name == path.name:
+                        counted = self._b200_access.get(codeobj.name, {}).get("counted")
+                        if counted:
+                            hits_n = int(counted["size"])
                 out.append(
                     {
                         "name": path.name,
                         "sources": self.dynamic_arrays[path.synapse_sources],
                         "start": int(path.source.start),
                         "stop": int(path.source.stop),
+                        "hits_n": hits_n,
                     }
                 )
         return out
@@ -858,9 +986,14 @@ class B200Device(CPPStandaloneDevice):
         # rebuilt (and re-uploaded) by the `_before_run_*_push_spikes()` of the next run.
         mutators = {"run_code_object", "set_by_constant", "set_by_array", "set_by_single_value",
                     "set_array_by_array", "resize_array"}
+        # (the clocks' t / timestep / dt are set before every run; pathways look at dt themselves)
+        clock_arrays = {self.arrays[var] for clock in self.clocks for var in clock.variables.values()
+                        if var in self.arrays}
         queue = []
         for func, args in self.main_queue:
             queue.append((func, args))
+            if func == "set_by_single_value" and args[0] in clock_arrays:
+                continue
             if func in mutators or (func == "insert_code" and "b200::state()" not in str(args)):
                 queue.append(("insert_code", "b200::state().host_epoch++;"))
         original, self.main_queue = self.main_queue, queue
@@ -939,26 +1072,36 @@ class B200Device(CPPStandaloneDevice):
                 writer.write(f"code_objects/{codeobj.name}.cpp", code)
             writer.write(f"code_objects/{codeobj.name}.h", codeobj.code.h_file)
 
-        # persistent kernels: one per run() call
+        # persistent kernels: one per run() call (two variants if delayed-only pathways allow a
+        # cheaper schedule: chosen at run time, when the delays are known)
         plans = []
         for index, entries in enumerate(self._b200_plans):
             clocks = {clock for clock, _ in entries}
-            plan = {"index": index, "entries": [], "clock": None, "signature": "", "n_barriers": 0,
-                    "tail_publish": []}
+            plan = {"index": index, "variants": [], "clock": None, "signature": "", "n_barriers": 0}
             if len(clocks) == 1 and prefs.devices.b200.persistent and not self.enable_profiling_any:
                 clock = next(iter(clocks))
                 try:
-                    items = self._plan_barriers(entries)
-                    for it in items:
-                        it["name"] = alias_of.get(it["name"], it["name"])
-                    plan["entries"] = items
-                    plan["tail_publish"] = list(self._b200_tail_publish)
+                    for tag in ("d0", "d1"):
+                        items, end_barrier = self._plan_barriers(entries, variant=tag)
+                        for it in items:
+                            it["name"] = alias_of.get(it["name"], it["name"])
+                        signature = " ".join(
+                            ("| " if it["barrier"] else "") + it["name"] + ("@apply" if it["kind"] == "apply" else "")
+                            for it in items
+                        ) + (" |" if end_barrier else "")
+                        variant = {"tag": tag, "entries": items, "end_barrier": end_barrier,
+                                   "signature": signature,
+                                   "n_barriers": sum(1 for it in items if it["barrier"]) + (1 if end_barrier else 0)}
+                        if plan["variants"] and plan["variants"][0]["signature"] == signature:
+                            continue     # delays make no difference to this schedule
+                        plan["variants"].append(variant)
                     plan["clock"] = clock.name
-                    plan["signature"] = " ".join(
-                        ("| " if it["barrier"] else "") + it["name"] for it in items
-                    )
-                    plan["n_barriers"] = 1 + sum(1 for it in items if it["barrier"])
+                    plan["signature"] = " // ".join(f"[{v['tag']}] {v['signature']}" for v in plan["variants"])
+                    plan["n_barriers"] = plan["variants"][0]["n_barriers"]
+                    # (kept for introspection / tests: the conservative variant)
+                    plan["entries"] = plan["variants"][0]["entries"]
                 except NotImplementedError as ex:
+                    plan["variants"] = []
                     logger.warn(f"run #{index} falls back to stepwise execution: {ex}")
             # run() calls with an identical schedule share one kernel
             plan["alias"] = None
@@ -1056,6 +1199,7 @@ class B200Device(CPPStandaloneDevice):
         lib.set_option("max_chunk", int(prefs.devices.b200.max_chunk))
         lib.set_option("ctas_per_sm", int(prefs.devices.b200.ctas_per_sm))
         lib.set_option("grid", int(prefs.devices.b200.grid))
+        lib.set_option("allow_d1", 1 if prefs.devices.b200.elide_end_barrier else 0)
         comm = self.communicator()
         if comm.world > 1:
             self._check_multi_gpu_support()
@@ -1247,10 +1391,12 @@ class B200Device(CPPStandaloneDevice):
         info = self._b200_plan_info[plan]
         if info["alias"] is not None:
             info = self._b200_plan_info[info["alias"]]
+        variant = info["variants"][-1] if (len(info["variants"]) > 1 and self.counter("all_delayed") > 0) \
+            else info["variants"][0]
         names = []
-        for it in info["entries"]:
-            names += ["barrier" if it["barrier"] else None, it["name"]]
-        names.append("end-of-step barrier")
+        for it in variant["entries"]:
+            names += ["barrier" if it["barrier"] else None, it["name"] + ("@apply" if it["kind"] == "apply" else "")]
+        names.append("end-of-step barrier" if variant["end_barrier"] else "end of step (no barrier)")
         if not all_ctas:
             return [(n, self.counter(f"phase{i}")) for i, n in enumerate(names) if n is not None]
         # cycles of the four sampled CTAs (first, 1/4, 3/4, last of the grid)

@@ -110,23 +110,26 @@ void _run_{{name}}() { _run_{{rep}}(); }   // same source as {{rep}} (created by
 
 {% for plan in plans %}
 {% if plan.clock and plan.alias is not none %}
-// run() call #{{plan.index}} has the same schedule as #{{plan.alias}}: shares its kernel
+// run() call #{{plan.index}} has the same schedule as #{{plan.alias}}: shares its kernels
 const B200Plan _b200_plan_{{plan.index}} = { _b200_run_chunk_{{plan.alias}}, "{{plan.signature}}" };
 {% elif plan.clock %}
 // =============================================================================================
-// persistent step kernel for run() call #{{plan.index}}
-//   schedule: {{plan.signature}}
-//   grid barriers per step: {{plan.n_barriers}} (incl. the end-of-step barrier)
+// persistent step kernel(s) for run() call #{{plan.index}}
+{% for v in plan.variants %}
+//   [{{v.tag}}] schedule: {{v.signature}}
+//   [{{v.tag}}] grid barriers per step: {{v.n_barriers}}{{ '' if v.end_barrier else ' (no end-of-step barrier)' }}
+{% endfor %}
 // =============================================================================================
 struct _B200Scal_{{plan.index}} {
-    {% for item in plan.entries if item.kind == 'codeobj' %}
+    {% for item in plan.variants[0].entries if item.kind == 'codeobj' %}
     _co_{{item.name}}::Scal {{item.name}};
     {% endfor %}
     int _unused;
 };
 
+{% for v in plan.variants %}
 __global__ void __launch_bounds__(b200::kBlock, {{ctas_per_sm}})
-_b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
+_b200_persistent_{{plan.index}}_{{v.tag}}(const _B200Clocks _clks0, const long long _nsteps, const _B200Scal_{{plan.index}} _sc)
 {
     const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
     unsigned long long _bar_target = 0ULL;
@@ -143,13 +146,14 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     {% endif %}
     while (_step < _nsteps)
     {
+        bool _stop = false;
         // the stop flag lives in host memory (one PCIe round trip per poll): look at it every
         // 64 steps only -- a stop request is honoured within a few milliseconds
         if ((_step & 63) == 0 && _ctx.bid == 0 && threadIdx.x == 0 && b200::ld_volatile_s32(_A._stop_request))
             b200::raise_stop(_A._ctrl);
-        {% for item in plan.entries %}
+        {% for item in v.entries %}
         {% if item.barrier %}
-        b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        _stop |= b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
         B200_PHASE({{2 * loop.index0}})
         {% elif not loop.first %}
         __syncthreads();
@@ -172,13 +176,21 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
         }
         {% elif item.kind == 'compact' %}
         b200::compact_segments(_A._es{{item.es}}, _clks.{{item.clock}}.timestep, _ctx, _A._ctrl);
+        {% elif item.kind == 'apply' %}
+        _dev_{{item.name}}_apply(_ctx, _clks, _sc.{{item.name}});
         {% else %}
         _dev_{{item.name}}(_ctx, _clks, _sc.{{item.name}});
         {% endif %}
         B200_PHASE({{2 * loop.index0 + 1}})
         {% endfor %}
-        const bool _stop = b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
-        B200_PHASE({{2 * (plan.entries | length)}})
+        {% if v.end_barrier %}
+        _stop |= b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
+        {% else %}
+        // no end-of-step barrier: nothing in the first phase of the next step depends on the
+        // last phase of this one across CTAs (B200Device._plan_barriers)
+        __syncthreads();
+        {% endif %}
+        B200_PHASE({{2 * (v.entries | length)}})
         // Clock::tick (brianlib/clocks.h:34-38)
         _clks.{{plan.clock}}.timestep += 1;
         _clks.{{plan.clock}}.t = _clks.{{plan.clock}}.timestep * _clks.{{plan.clock}}.dt;
@@ -188,21 +200,14 @@ _b200_persistent_{{plan.index}}(const _B200Clocks _clks0, const long long _nstep
     if (_ctx.bid == 0 && threadIdx.x == 0) _A._ctrl->steps_done = (int)_step;
 }
 #undef B200_PHASE
-B200_REGISTER_KERNEL(_b200_persistent_{{plan.index}})
-{% if profile_phases %}
-// names of the profiled phases of plan #{{plan.index}} (index = slot in _A._prof)
-const char* _b200_phase_names_{{plan.index}}[] = {
-    {% for item in plan.entries %}
-    "{{ 'barrier' if item.barrier else '-' }}", "{{item.name}}",
-    {% endfor %}
-    "end-of-step barrier", 0 };
-{% endif %}
+B200_REGISTER_KERNEL(_b200_persistent_{{plan.index}}_{{v.tag}})
+{% endfor %}
 
 static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
 {
     b200::RuntimeState& st = b200::state();
     _B200Scal_{{plan.index}} sc;
-    {% for item in plan.entries if item.kind == 'codeobj' %}
+    {% for item in plan.variants[0].entries if item.kind == 'codeobj' %}
     _hostscal_{{item.name}}(sc.{{item.name}});
     {% endfor %}
     sc._unused = 0;
@@ -211,8 +216,14 @@ static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
     _B200Clocks clks = _b200_clocks_now();
     void* args[] = {(void*)&clks, (void*)&nsteps, (void*)&sc};
     const int grid = _b200_grid_size();
+    // 'd1': every pathway delivers at least one step after the spike (decided at upload)
+    {% if plan.variants | length > 1 %}
+    const void* kernel = st.all_delayed ? (const void*)_b200_persistent_{{plan.index}}_d1 : (const void*)_b200_persistent_{{plan.index}}_d0;
+    {% else %}
+    const void* kernel = (const void*)_b200_persistent_{{plan.index}}_{{plan.variants[0].tag}};
+    {% endif %}
     _b200_launch_begin("persistent_{{plan.index}}");
-    B200_CUDA(cudaLaunchCooperativeKernel((const void*)_b200_persistent_{{plan.index}}, dim3(grid), dim3(b200::kBlock), args, 0, st.stream));
+    B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(b200::kBlock), args, 0, st.stream));
     _b200_launch_end("persistent_{{plan.index}}");
     B200_CUDA(cudaMemcpyAsync(st.control_host, st.control, sizeof(b200::Control), cudaMemcpyDeviceToHost, st.stream));
     B200_CUDA(cudaStreamSynchronize(st.stream));

@@ -103,6 +103,7 @@ b200::TargetIndex _b200_sv_{{sv}};
 static long long _monN_ub_{{mon.name}} = 0;
 {% endfor %}
 static bool _b200_first_upload = true;
+bool _b200_allow_d1 = true;      // prefs.devices.b200.elide_end_barrier
 // monitor records: number of leading elements identical on host and device (see upload_records)
 {% for a in b200_arrays %}
 {% if a.used and a.kind == 'dynamic1d' and a.monitor %}
@@ -179,6 +180,22 @@ void _b200_upload()
     }
     _A_host._rank = st.rank;
     _A_host._world = st.world;
+    {   // does every pathway deliver at least one step after the spike?  (-> 'd1' step kernels)
+        bool _any = false, _all = _b200_allow_d1;
+        {% for pw in b200_pathways %}
+        if (brian::{{pw.name}}.prepared) {
+            _any = true;
+            if (brian::{{pw.name}}.bin_delay.empty() || brian::{{pw.name}}.bin_delay.front() < 1) _all = false;
+            brian::{{pw.name}}.ensure_hits({{pw.hits_n}});
+        }
+        {% endfor %}
+        {% for es in b200_eventspaces %}
+        {% if es.compact_always %}
+        _all = false;   // order-dependent synaptic code walks the current step's compacted list
+        {% endif %}
+        {% endfor %}
+        st.all_delayed = _any && _all;
+    }
     {% for es in b200_eventspaces %}
     _b200_es{{es.name}}.id = {{loop.index}};
     _b200_es{{es.name}}.compact_always = {{ 'true' if es.compact_always else 'false' }};
@@ -226,11 +243,11 @@ void _b200_prepare_steps(long long steps, bool exact)
         {% if mon.kind == 'spike' %}
         // worst case one entry per source neuron per step; the kernel raises `overflow` when
         // fewer than one step's worst case of slots is free
-        long long _need = _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * (exact ? 2 : 1);
+        long long _need = _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * (exact ? 3 : 1);
         // a launch of `steps` steps at the event rate seen so far (x1.5) should fit without
         // interrupting the persistent kernel for a buffer growth
         if (exact && _b200_steps_prepared > 0 && steps > 1)
-            _need = std::max(_need, _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * 2 +
+            _need = std::max(_need, _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * 3 +
                                     (long long)(1.5 * (double)_monN_ub_{{mon.name}} / (double)_b200_steps_prepared * (double)steps));
         {% else %}
         long long _need = _monN_ub_{{mon.name}} + steps;
@@ -242,7 +259,7 @@ void _b200_prepare_steps(long long steps, bool exact)
                 B200_CUDA(cudaMemcpy(_two, _A_host._monN_{{mon.name}}, sizeof(_two), cudaMemcpyDeviceToHost));
                 _monN_ub_{{mon.name}} = std::max(_two[0], _two[1]);
                 {% if mon.kind == 'spike' %}
-                _need = _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * 2;
+                _need = _monN_ub_{{mon.name}} + (long long){{mon.headroom}} * 3;
                 {% else %}
                 _need = _monN_ub_{{mon.name}} + steps;
                 {% endif %}

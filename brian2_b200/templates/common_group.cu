@@ -77,6 +77,9 @@ void _run_{{codeobj_name}}()
 #ifndef _INCLUDED_{{codeobj_name}}
 #define _INCLUDED_{{codeobj_name}}
 void _run_{{codeobj_name}}();
+{% if b200_counted %}
+void _run_{{codeobj_name}}_apply();   // apply pass of a counted pathway (see synapses.cu)
+{% endif %}
 #endif
 {% endmacro %}
 

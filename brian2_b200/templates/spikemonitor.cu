@@ -49,7 +49,8 @@
         {{N}} = (int32_t)_N_new;
         {% if record_variables %}
         {% set _first = (record_variables | dictsort | first)[1] %}
-        if (_N_new + (long long)(_source_stop - _source_start) > (long long)_A._cap{{b200_field(_first)}})
+        // (a stop raised here takes effect at the next grid barrier, which may be one step away)
+        if (_N_new + 2LL * (long long)(_source_stop - _source_start) > (long long)_A._cap{{b200_field(_first)}})
         {
             _A._ctrl->overflow = 1;
             b200::raise_stop(_A._ctrl);

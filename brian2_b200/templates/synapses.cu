@@ -45,6 +45,11 @@
         }
     }
     {% else %}
+    {% if b200_counted %}
+    // counted pathway: the delivery only counts the events per target (integer reductions);
+    // the owner of every target applies them afterwards (_dev_{{codeobj_name}}_apply below)
+    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    {% endif %}
     const int _lane = threadIdx.x & 31;
     const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
     const int _nwarps = _ctx.nb * b200::kWarps;
@@ -60,11 +65,13 @@
         _bdelay0 = __ldg(_pw.bin_delay + _lane);
         _blr0 = (__ldg(_pw.bin_maxlen + _lane) + 62) >> 5;
     }
-    // The list of the current step (delay 0) is read from the thresholder's segments
+    // The youngest list (delay 0; delay 1 when every pathway of the project is delayed) is read
+    // straight from the thresholder's segments
+    const int _segd = _pw.seg_delay;
     b200::SpikeView _view;
     _view.total = 0;
-    if (_pw.has_delay0)
-        _view = b200::view_build(_es, _b200_timestep, _ctx, false, _A._ctrl);
+    if (_segd >= 0)
+        _view = b200::view_build(_es, _b200_timestep - _segd, _ctx, false, _A._ctrl);
     // Work = 128-byte lines of the packed index stream.  Every (delay bin, spike of that bin's
     // step) row is padded to the bin's longest row (`_lr` lines of 32 slots, on 32-slot boundaries:
     // a warp load is one aligned line) and the lines of all rows of all bins form one virtual
@@ -83,7 +90,7 @@
             _bdelay = _g0 == 0 ? _bdelay0 : __ldg(_pw.bin_delay + _mybin);
             _blr = _g0 == 0 ? _blr0 : ((__ldg(_pw.bin_maxlen + _mybin) + 62) >> 5);
             if (_blr < 1) _blr = 1;
-            if (_bdelay == 0)
+            if (_bdelay == _segd)
                 _bn = _view.total;
             else
             {
@@ -150,7 +157,7 @@
                 int _len = 0, _rbeg = 0, _srcabs = 0;
                 if (_rv)
                 {
-                    const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
+                    const int _src = (_delay == _segd ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
                     if (_src >= 0 && _src < _pw.nsrc)
                     {
                         const int* _rp = _pw.rowptr + (size_t)(_g0 + _blo) * (_pw.nsrc + 1);
@@ -267,7 +274,7 @@
             // lines of this row inside my share
             const int _nl = (int)min((long long)(_lr - _l0), _b - _a);
             _a += _nl;
-            const int _src = (_delay == 0 ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
+            const int _src = (_delay == _segd ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
             if (_src < 0 || _src >= _pw.nsrc) continue;
             const int _rbeg = _rp[_src], _rend = _rp[_src + 1];
             if (_l0 == 0) _nev += (unsigned long long)(_rend - _rbeg);
@@ -326,4 +333,59 @@
     _nev += _nev_lane;
     if (_lane == 0 && _nev) atomicAdd(_pw.events, _nev);
     {% endif %}
+{% endblock %}
+
+{% block extra_device_code %}
+{% if b200_counted %}
+// ---- apply pass of the counted pathway: element-private, same partition as the state updater of
+// the target group.  The events of this pathway in this step are applied one after the other,
+// exactly like the reference's loop over the queue (synapses.cpp:20-49).
+__device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ctx, const _B200Clocks& _clks,
+                                                           const _co_{{codeobj_name}}::Scal& _sc)
+{
+    using namespace _co_{{codeobj_name}};
+    ///// CONSTANTS ///////////
+    %CONSTANTS_DEV%
+    ///// POINTERS ////////////
+    {{pointers_lines|autoindent}}
+    const b200::PathwayDev& _pw = _A._pw_{{pathway.name}};
+    const int64_t _b200_timestep = _clks.{{b200_clock}}.timestep;
+    // scalar code
+    {{scalar_code|autoindent}}
+    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    B200_FOR_OWNED(_i64, (int64_t){{b200_counted.size}}, _ctx)
+    {
+        const int _b200_tgt_idx = (int)_i64;
+        const int _b200_n = __ldcg(_b200_hits + _b200_tgt_idx);
+        if (_b200_n == 0) continue;
+        _b200_hits[_b200_tgt_idx] = 0;      // this buffer is counted into again two steps from now
+        const int _idx = _b200_tgt_idx;
+        const int _vectorisation_idx = _idx;
+        {{b200_apply_loads|autoindent}}
+        for (int _b200_k = 0; _b200_k < _b200_n; ++_b200_k)
+        {
+            {{b200_apply_body|autoindent}}
+        }
+        {{b200_apply_stores|autoindent}}
+    }
+}
+
+__global__ void __launch_bounds__(b200::kBlock, {{prefs.devices.b200.ctas_per_sm}})
+_kernel_{{codeobj_name}}_apply(const _B200Clocks _clks, const _co_{{codeobj_name}}::Scal _sc)
+{
+    const b200::Ctx _ctx{(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.x, (int)gridDim.x, _A._rank, _A._world};
+    b200::view_reset();
+    _dev_{{codeobj_name}}_apply(_ctx, _clks, _sc);
+}
+B200_REGISTER_KERNEL(_kernel_{{codeobj_name}}_apply)
+
+void _run_{{codeobj_name}}_apply()
+{
+    _co_{{codeobj_name}}::Scal _sc;
+    _hostscal_{{codeobj_name}}(_sc);
+    _b200_launch_begin("{{codeobj_name}}");
+    _kernel_{{codeobj_name}}_apply<<<_b200_grid_size(), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now(), _sc);
+    _b200_launch_end("{{codeobj_name}}");
+}
+{% endif %}
 {% endblock %}

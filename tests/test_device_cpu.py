@@ -55,26 +55,51 @@ def test_device_code_is_sm100a_sass(cuba_project):
     assert "sm_100a" in out, out
 
 
+def _schedules(src):
+    """{variant tag: (phases, barriers per step, has end-of-step barrier)} of the first plan."""
+    out = {}
+    for tag, sched in re.findall(r"//   \[(d\d)\] schedule: (.*)\n", src):
+        if tag in out:
+            continue
+        end = sched.rstrip().endswith("|")
+        phases = [p.split() for p in sched.rstrip().rstrip("|").split("|")]
+        n = int(re.search(rf"//   \[{tag}\] grid barriers per step: (\d+)", src).group(1))
+        out[tag] = (phases, n, end)
+    return out
+
+
 def test_barrier_plan_of_cuba(cuba_project):
-    """stateupdate -> threshold share the owned partition (no barrier); one barrier before the
-    consumers of the spike list (compaction, monitor, pathways; the resetter only touches the
-    CTA's own segment); one at the end of the step."""
-    src = open(os.path.join(cuba_project, "b200_kernels.cu")).read()
-    m = re.search(r"schedule: (.*)\n", src)
-    assert m
-    sched = m.group(1).strip()
-    assert sched == ("cuba_P_stateupdater_codeobject cuba_P_spike_thresholder_codeobject | "
-                     "cuba_spikes_codeobject cuba_Ce_pre_codeobject cuba_Ci_pre_codeobject "
-                     "cuba_P_spike_resetter_codeobject compact_array_cuba_P__spikespace"), sched
-    assert "grid barriers per step: 2" in src
+    """Phases of a CUBA step.  stateupdate -> threshold -> reset share the owned partition (no
+    barrier: the resetter only touches the CTA's own segment); one barrier before the consumers
+    of the spike list (monitor, the two counted deliveries, compaction); one before the owners
+    apply the counted events; NO barrier at the end of the step (the next state update only
+    meets element-private data).  With delays >= 1 step ('d1') the deliveries move in front of
+    the first barrier and one barrier per step is left."""
+    plans = _schedules(open(os.path.join(cuba_project, "b200_kernels.cu")).read())
+    phases, n, end = plans["d0"]
+    assert phases == [
+        ["cuba_P_stateupdater_codeobject", "cuba_P_spike_thresholder_codeobject", "cuba_P_spike_resetter_codeobject"],
+        ["cuba_spikes_codeobject", "cuba_Ce_pre_codeobject", "cuba_Ci_pre_codeobject",
+         "compact_array_cuba_P__spikespace"],
+        ["cuba_Ce_pre_codeobject@apply", "cuba_Ci_pre_codeobject@apply"]], phases
+    assert (n, end) == (2, False)
+    phases, n, end = plans["d1"]
+    assert phases[0][:4] == ["cuba_P_stateupdater_codeobject", "cuba_P_spike_thresholder_codeobject",
+                             "cuba_Ce_pre_codeobject", "cuba_Ci_pre_codeobject"], phases
+    assert (len(phases), n, end) == (2, 1, False)
 
 
-def test_synaptic_effect_uses_atomics_not_rmw(cuba_project):
+def test_constant_synaptic_effect_is_counted_not_accumulated_in_floating_point(cuba_project):
+    """`ge_post += we` touches target-side data only: the delivery counts events per target with
+    integer reductions and the owner of the target applies `ge += we` that many times -- the
+    reference's sequential read-modify-write survives only inside that element-private loop."""
     code = open(os.path.join(cuba_project, "code_objects", "cuba_Ce_pre_codeobject.cuh")).read()
-    assert "b200::atomic_add(&_ptr_array_cuba_P_ge[_postsynaptic_idx]" in code
-    # the reference's sequential read-modify-write must not survive in device code
-    dev = code.split("__device__ __forceinline__ void _dev_")[1].split("__global__")[0]
-    assert "ge[_postsynaptic_idx] = ge" not in dev.replace("_ptr_array_cuba_P_", "")
+    deliver = code.split("__device__ __forceinline__ void _dev_cuba_Ce_pre_codeobject(")[1].split("__global__")[0]
+    assert "atomicAdd(_b200_hits + _b200_tgt_idx, 1);" in deliver
+    assert "_ptr_array_cuba_P_ge[" not in deliver.split("// scalar code")[1]
+    apply = code.split("void _dev_cuba_Ce_pre_codeobject_apply(")[1].split("__global__")[0]
+    assert "for (int _b200_k = 0; _b200_k < _b200_n; ++_b200_k)" in apply
+    assert "ge += we;" in apply and "_ptr_array_cuba_P_ge[_postsynaptic_idx] = ge;" in apply
 
 
 def test_no_cpu_fallback_without_gpu(cuba_project):
@@ -252,38 +277,47 @@ def test_generated_propagation_code_of_ragged_case(ragged_project):
     assert "const int32_t _presynaptic_idx = _b200_tgt_idx;" in post     # on_post: the other end is pre
     assert "b200::atomic_add(&_ptr_array_rg_neurons_y[_presynaptic_idx]" in post
     assert "_ptr_array_rg_S_w[_idx] = w;" in post
-    # three grid barriers: spikes -> on_pre -> on_post (reads what on_pre wrote) -> end of step
-    src = open(os.path.join(ragged_project, "b200_kernels.cu")).read()
-    assert "grid barriers per step: 3" in src
+    # spikes -> on_pre -> on_post (reads `w`, which on_pre ... does not write here: same phase is
+    # fine; on_post writes `w` that on_pre reads -> barrier): two barriers, none at the end
+    plans = _schedules(open(os.path.join(ragged_project, "b200_kernels.cu")).read())
+    phases, n, end = plans["d0"]
+    assert "rg_S_pre_codeobject" in phases[1] and phases[2] == ["rg_S_post_codeobject"], phases
+    assert n == 2 and not end
 
 
-def _schedule_of(case):
+def _plans_of(case):
     import __graft_entry__ as ge
 
     directory, _ = ge.build_project(case, directory=os.path.join(ge.PREBUILT, "cpu_" + case))
-    src = open(os.path.join(directory, "b200_kernels.cu")).read()
-    return re.search(r"schedule: (.*)\n", src).group(1).strip(), src
+    return _schedules(open(os.path.join(directory, "b200_kernels.cu")).read())
 
 
 def test_barrier_plan_of_brunel(brian):
-    """`v += J` (exc) and `v += -g*J` (inh) scatter into the same array: the deliveries must not
-    interleave if `v` is to stay bit-identical with the reference (which delivers all of exc, then
-    all of inh), and the resetter's private write `v = V_r` must follow both: 4 barriers."""
-    sched, src = _schedule_of("brunel_hetero")
-    phases = [p.split() for p in sched.split("|")]
-    assert [len(p) for p in phases] == [2, 2, 1, 3], sched
-    assert phases[1][-1] == "brunel_exc_pre_codeobject" and phases[2] == ["brunel_inh_pre_codeobject"]
-    assert phases[3][0] == "brunel_neurons_spike_resetter_codeobject"
-    assert "grid barriers per step: 4" in src
+    """`v += J` (exc) and `v += -g*J` (inh) only read target-side data (`not_refractory`): both
+    are counted, so they may deliver side by side and the owner applies exc, then inh, then the
+    reset -- the reference's order, bit-identical `v`, no floating-point atomics.  With the
+    heterogeneous delays of the model (>= 1 step, 'd1') the deliveries overlap the state update
+    and ONE grid barrier per step is left (round 1: four)."""
+    plans = _plans_of("brunel_hetero")
+    phases, n, end = plans["d0"]
+    assert [len(p) for p in phases] == [2, 5, 3] and (n, end) == (2, False), phases
+    assert phases[2] == ["brunel_exc_pre_codeobject@apply", "brunel_inh_pre_codeobject@apply",
+                         "brunel_neurons_spike_resetter_codeobject"]
+    phases, n, end = plans["d1"]
+    assert phases[0] == ["brunel_neurons_stateupdater_codeobject", "brunel_neurons_spike_thresholder_codeobject",
+                         "brunel_exc_pre_codeobject", "brunel_inh_pre_codeobject"], phases
+    assert phases[1][1:4] == ["brunel_exc_pre_codeobject@apply", "brunel_inh_pre_codeobject@apply",
+                              "brunel_neurons_spike_resetter_codeobject"], phases
+    assert (len(phases), n, end) == (2, 1, False)
 
 
 def test_barrier_plan_of_stdp(brian):
     """on_pre (order -1) and on_post (order +1) of one Synapses object touch the same synaptic
     variables (`w`, `Apre`, `Apost`, `lastupdate`): a barrier separates them; both thresholders
-    share the first phase with both state updaters (element-private chains)."""
-    sched, src = _schedule_of("stdp_1000")
-    phases = [p.split() for p in sched.split("|")]
-    assert len(phases) == 3, sched
+    share the first phase with both state updaters (element-private chains); the next step's
+    state update reads `ge`, which on_pre accumulates with atomics: end-of-step barrier."""
+    phases, n, end = _plans_of("stdp_1000")["d0"]
+    assert len(phases) == 3, phases
     assert "stdp_S_pre_codeobject" in phases[1] and phases[2][0] == "stdp_S_post_codeobject"
     assert {"stdp_inputs_stateupdater_codeobject", "stdp_neurons_spike_thresholder_codeobject"} <= set(phases[0])
-    assert "grid barriers per step: 3" in src
+    assert (n, end) == (3, True)

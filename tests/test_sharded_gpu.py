@@ -46,8 +46,10 @@ def test_connect_p_statistics(brian, project_dir):
         assert np.all(np.diff(key) > 0), "synapses must be sorted by (pre, post) without duplicates"
         out_deg = np.bincount(i, minlength=n_pre)
         in_deg = np.bincount(j, minlength=N)
-        assert np.array_equal(out_deg, np.asarray(S.N_outgoing_pre[:]))
-        assert np.array_equal(in_deg, np.asarray(S.N_incoming_post[:]))
+        # (the counters are indexed by the ABSOLUTE index in the parent group, like the reference's:
+        # synapses_create_generator.cpp:22-23 sizes them N + offset)
+        assert np.array_equal(out_deg, np.asarray(S.N_outgoing_pre[:])[-n_pre:])
+        assert np.array_equal(in_deg, np.asarray(S.N_incoming_post[:])[-N:])
         # binomial degrees: mean and variance (variance of a sample variance ~ 2 sigma^4 / n)
         for deg, n_other, n_rows in ((out_deg, N, n_pre), (in_deg, n_pre, N)):
             mean, var = n_other * eps, n_other * eps * (1 - eps)
