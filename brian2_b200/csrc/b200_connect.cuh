@@ -90,6 +90,12 @@ struct CandidateIter {
     }
 };
 
+// stands in for a group's index array `i` (an arange array) inside connect kernels
+struct IdentityIndex {
+    int start;
+    __device__ __forceinline__ int32_t operator[](long long k) const { return (int32_t)(start + k); }
+};
+
 // what one row does with an accepted (pre, post, multiplicity) triple
 struct RowSink {
     const ConnectArgs& a;

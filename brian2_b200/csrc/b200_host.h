@@ -404,6 +404,9 @@ public:
     unsigned int* d_tickets = nullptr;
     int* d_hits = nullptr;
     int hits_n = 0;
+    int* d_tileptr = nullptr;      // b200_tiles.cuh
+    int tile_stride = 0, tiles_grid = 0;
+    bool tiles_tried = false;      // since the CSR was last built
     EventSpace* es = nullptr;
     size_t n_owned = 0;            // synapses stored on this rank (post neuron owned)
 
@@ -414,7 +417,9 @@ public:
 
     void release() {
         dev_free(d_bin_delay); dev_free(d_rowptr); dev_free(d_syn_ids); dev_free(d_csr_target);
-        d_bin_delay = d_rowptr = d_syn_ids = d_csr_target = nullptr;
+        dev_free(d_tileptr);
+        d_bin_delay = d_rowptr = d_syn_ids = d_csr_target = d_tileptr = nullptr;
+        tiles_tried = false;
     }
 
     // Build the delay-binned CSR.  Delay rounding as CSpikeQueue::prepare (spikequeue.h:90):
@@ -562,6 +567,8 @@ public:
         v.seg_delay = (!bin_delay.empty() && bin_delay.front() == seg) ? seg : -1;
         v.hits = d_hits;
         v.hits_n = hits_n;
+        v.tileptr = d_tileptr;
+        v.tile_stride = tile_stride;
         v.bin_delay = d_bin_delay;
         v.bin_maxlen = d_bin_delay + nbins;
         v.rowptr = d_rowptr;

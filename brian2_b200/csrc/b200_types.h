@@ -70,6 +70,9 @@ struct PathwayDev {
                               // thresholder's segments, -1: none (older lists: compacted form)
     int* hits;                // counted pathways: [2][hits_n] events per target, by step parity
     int hits_n;
+    const int* tileptr;       // dense rows (b200_tiles.cuh): [nbins][nsrc + 1][grid + 1] first slot of
+                              // the row at or after the first target of every CTA's block; 0: none
+    int tile_stride;          // ints between the per-warp counter arrays in shared memory
     const int* bin_delay;     // [nbins] delay in steps, ascending
     const int* bin_maxlen;    // [nbins] length of the longest row of the bin
     const int* rowptr;        // [nbins*(nsrc+1)+1] slot offsets

@@ -495,7 +495,18 @@ class CUDACodeGenerator(CPPCodeGenerator):
                 # the device version of connect() evaluates index arithmetic and rand() only;
                 # conditions that read state variables of the connected groups need the
                 # reference's host path (prefs.devices.b200.construction = 'reference')
-                touched = sorted(ve_read | ve_write | sc_read | ve_indices | sc_indices)
+                # ... and the index arrays `i` of the connected groups (arange arrays: the value
+                # IS the index), which subgroup sources / targets bring in
+                identity = getattr(self, "_b200_identity_arrays", {})
+                aranges = {v: start for v, _, start in self.device.arange_arrays}
+                for name in sorted(ve_read | sc_read):
+                    var = self.variables[name]
+                    start = aranges.get(var) if name not in ve_write else None
+                    if start is not None:
+                        identity[self.get_array_name(var)] = int(start)
+                self._b200_identity_arrays = identity
+                touched = sorted(n for n in (ve_read | ve_write | sc_read | ve_indices | sc_indices)
+                                 if self.get_array_name(self.variables[n]) not in identity)
                 if touched:
                     raise NotImplementedError(
                         "b200 sharded construction: connect() expressions that read arrays "
@@ -581,6 +592,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
             scal_host, scal_members = scal_host[None], scal_members[None]
         kwds["b200_scalar_host"] = scal_host
         kwds["b200_scalar_members"] = scal_members
+        kwds["b200_identity_arrays"] = sorted(getattr(self, "_b200_identity_arrays", {}).items())
         kwds["b200_counted"] = access.get("counted")
         kwds["b200_serial"] = serial
         kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)

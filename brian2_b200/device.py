@@ -139,6 +139,15 @@ prefs.register_preferences(
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
+    tiled_delivery=BrianPreference(
+        default=True,
+        docs="""
+        Counted pathways whose rows are dense (on average at least 8 synapses of a row point into
+        the block of targets of every CTA): cut the rows at the CTAs' block boundaries when the
+        CSR is built and let the owner of every block count its events in shared memory
+        (csrc/b200_tiles.cuh) instead of scattering integer reductions through L2.
+        """,
+    ),
     elide_end_barrier=BrianPreference(
         default=True,
         docs="""
@@ -942,6 +951,7 @@ class B200Device(CPPStandaloneDevice):
     def generate_objects_source(
         self, writer, arange_arrays, synapses, static_array_specs, networks, timed_arrays
     ):
+        self._b200_synapses_objects = list(synapses)
         # host mirrors: the reference's own objects.cpp, minus its SynapticPathway objects
         host_tmp = CPPStandaloneCodeObject.templater.objects(
             None,
@@ -1117,8 +1127,10 @@ class B200Device(CPPStandaloneDevice):
             None,
             None,
             device_code_objects=device_objs,
-            code_object_aliases=sorted(alias_of.items()),
+            code_object_aliases=[(name, rep, bool(self._b200_access.get(name, {}).get("counted")))
+                                 for name, rep in sorted(alias_of.items())],
             b200_eventspaces=self._eventspaces(),
+            b200_pathways=self._pathways(self._b200_synapses_objects),
             plans=[p for p in plans],
             user_headers=user_headers,
             profiled=bool(self.enable_profiling_any),
@@ -1200,6 +1212,7 @@ class B200Device(CPPStandaloneDevice):
         lib.set_option("ctas_per_sm", int(prefs.devices.b200.ctas_per_sm))
         lib.set_option("grid", int(prefs.devices.b200.grid))
         lib.set_option("allow_d1", 1 if prefs.devices.b200.elide_end_barrier else 0)
+        lib.set_option("tiles", 1 if prefs.devices.b200.tiled_delivery else 0)
         comm = self.communicator()
         if comm.world > 1:
             self._check_multi_gpu_support()

@@ -5,6 +5,7 @@
 #include "b200_runtime.cuh"
 #include "b200_functions.cuh"
 #include "b200_connect.cuh"
+#include "b200_tiles.cuh"
 #include "network.h"
 #include "b200_plans.h"
 #include <cooperative_groups.h>
@@ -64,16 +65,21 @@ static std::vector<const void*>& _b200_all_kernels()
 struct _B200KernelRegistrar { _B200KernelRegistrar(const void* f) { _b200_all_kernels().push_back(f); } };
 #define B200_REGISTER_KERNEL(f) static _B200KernelRegistrar _b200_reg_##f((const void*)f);
 
+int _b200_dyn_smem = 0;          // dynamic shared memory of every kernel (tiles of dense counted pathways)
+bool _b200_allow_tiles = true;   // prefs.devices.b200.tiled_delivery
+
 int _b200_grid_size()
 {
-    static int grid = 0, ov = -1, cps = -1;
-    if (grid && ov == _b200_grid_override && cps == _b200_ctas_per_sm) return grid;
+    static int grid = 0, ov = -1, cps = -1, smem = -1;
+    if (grid && ov == _b200_grid_override && cps == _b200_ctas_per_sm && smem == _b200_dyn_smem) return grid;
     b200::runtime_init();
-    ov = _b200_grid_override; cps = _b200_ctas_per_sm;
+    ov = _b200_grid_override; cps = _b200_ctas_per_sm; smem = _b200_dyn_smem;
     int per_sm = _b200_ctas_per_sm;
     for (size_t i = 0; i < _b200_all_kernels().size(); i++) {
         int occ = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, _b200_all_kernels()[i], b200::kBlock, 0));
+        if (_b200_dyn_smem > 0)
+            B200_CUDA(cudaFuncSetAttribute(_b200_all_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, _b200_dyn_smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, _b200_all_kernels()[i], b200::kBlock, _b200_dyn_smem));
         if (occ < 1) throw std::runtime_error("b200: kernel cannot be resident (registers/shared memory)");
         per_sm = std::min(per_sm, occ);
     }
@@ -81,6 +87,32 @@ int _b200_grid_size()
     if (_b200_grid_override > 0) grid = std::min(grid, _b200_grid_override);
     grid = std::max(1, std::min(grid, b200::kBlock));
     return grid;
+}
+
+// ---- target tiles of dense counted pathways (csrc/b200_tiles.cuh); called by _b200_upload ----
+void _b200_tiles_reserve()
+{
+    bool any = false;
+    {% for pw in b200_pathways %}
+    {% if pw.hits_n %}
+    any = any || b200::tiles_candidate(brian::{{pw.name}}, 2 * b200::state().num_sms);
+    {% endif %}
+    {% endfor %}
+    _b200_dyn_smem = (any && _b200_allow_tiles) ? (int)b200::kTileSmem : 0;
+}
+void _b200_tiles_build()
+{
+    const int grid = _b200_grid_size();
+    (void)grid;
+    {% for pw in b200_pathways %}
+    {% if pw.hits_n %}
+    if (brian::{{pw.name}}.prepared && (!brian::{{pw.name}}.tiles_tried || brian::{{pw.name}}.tiles_grid != grid)) {
+        b200::tiles_build(brian::{{pw.name}}, grid, (size_t)_b200_dyn_smem);
+        brian::{{pw.name}}.tiles_tried = true;
+        brian::{{pw.name}}.tiles_grid = grid;
+    }
+    {% endif %}
+    {% endfor %}
 }
 
 // ---- implicit companions of the thresholders: compaction of an event space (stepwise mode) ----
@@ -104,8 +136,11 @@ void _run_b200_compact{{es.name}}()
 {% for codeobj in device_code_objects %}
 #include "code_objects/{{codeobj.name}}.cuh"
 {% endfor %}
-{% for name, rep in code_object_aliases %}
+{% for name, rep, counted in code_object_aliases %}
 void _run_{{name}}() { _run_{{rep}}(); }   // same source as {{rep}} (created by a later run() call)
+{% if counted %}
+void _run_{{name}}_apply() { _run_{{rep}}_apply(); }
+{% endif %}
 {% endfor %}
 
 {% for plan in plans %}
@@ -223,7 +258,7 @@ static long long _b200_run_chunk_{{plan.index}}(long long nsteps)
     const void* kernel = (const void*)_b200_persistent_{{plan.index}}_{{plan.variants[0].tag}};
     {% endif %}
     _b200_launch_begin("persistent_{{plan.index}}");
-    B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(b200::kBlock), args, 0, st.stream));
+    B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(b200::kBlock), args, _b200_dyn_smem, st.stream));
     _b200_launch_end("persistent_{{plan.index}}");
     B200_CUDA(cudaMemcpyAsync(st.control_host, st.control, sizeof(b200::Control), cudaMemcpyDeviceToHost, st.stream));
     B200_CUDA(cudaStreamSynchronize(st.stream));

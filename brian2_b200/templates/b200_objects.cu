@@ -62,6 +62,9 @@ void _b200_upload();
 void _b200_download();
 void _b200_sync_constants();                 // defined next to the kernels (owns __constant__ _A)
 int _b200_grid_size();                       // CTAs of every kernel of this project (co-resident)
+extern int _b200_dyn_smem;                   // dynamic shared memory of every kernel launch
+void _b200_tiles_reserve();                  // dense counted pathways: shared-memory budget ...
+void _b200_tiles_build();                    // ... and tile tables (csrc/b200_tiles.cuh)
 _B200Clocks _b200_clocks_now();
 void _b200_prepare_steps(long long steps, bool exact);   // make monitor buffers large enough
 void _b200_prefault_start(long long steps);   // host-side: map the pages the next records will land in
@@ -196,6 +199,8 @@ void _b200_upload()
         {% endfor %}
         st.all_delayed = _any && _all;
     }
+    _b200_tiles_reserve();      // (before the first _b200_grid_size(): occupancy depends on it)
+    _b200_tiles_build();
     {% for es in b200_eventspaces %}
     _b200_es{{es.name}}.id = {{loop.index}};
     _b200_es{{es.name}}.compact_always = {{ 'true' if es.compact_always else 'false' }};

@@ -34,7 +34,9 @@ extern std::map<std::string, double> _b200_prof_seconds;
 extern bool _b200_profiling;
 extern int _b200_ctas_per_sm;
 extern int _b200_grid_override;
+extern int _b200_dyn_smem;
 extern bool _b200_allow_d1;
+extern bool _b200_allow_tiles;
 
 static std::string _b200_error;
 
@@ -142,6 +144,7 @@ int b200_set_option(const char* key, double value)
     else if (k == "ctas_per_sm") _b200_ctas_per_sm = (int)value;
     else if (k == "grid") _b200_grid_override = (int)value;
     else if (k == "allow_d1") _b200_allow_d1 = value != 0;
+    else if (k == "tiles") _b200_allow_tiles = value != 0;
     else if (k == "seed") { b200::state().seed = (unsigned long long)value; b200::state().seeded = true; }
     else return 1;
     return 0;
@@ -164,6 +167,7 @@ double b200_get_counter(const char* key)
     if (k == "fence_cycles") return st.fence_cycles;
     if (k == "polls") return st.polls;
     if (k == "all_delayed") return st.all_delayed ? 1.0 : 0.0;
+    if (k == "dyn_smem") return (double)_b200_dyn_smem;
     if (k == "connect_seconds") return st.connect_seconds;
     if (k == "connect_synapses") return st.connect_synapses;
     if (k == "connect_launches") return (double)st.connect_launches;

@@ -49,6 +49,7 @@
     // counted pathway: the delivery only counts the events per target (integer reductions);
     // the owner of every target applies them afterwards (_dev_{{codeobj_name}}_apply below)
     int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    if (_pw.tileptr) return;    // dense rows: counted AND applied by the owners of the targets (apply pass)
     {% endif %}
     const int _lane = threadIdx.x & 31;
     const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
@@ -352,6 +353,114 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
     const int64_t _b200_timestep = _clks.{{b200_clock}}.timestep;
     // scalar code
     {{scalar_code|autoindent}}
+    if (_pw.tileptr)
+    {
+        // ---- dense rows: OWNER-COMPUTES in shared memory.  The targets of this CTA (its block of
+        // the element partition) are a tile; every (delay bin, source) row was cut at the tile
+        // boundaries when the CSR was built (`tileptr`), so this CTA reads exactly the entries of
+        // every spiking row that point into its tile -- contiguous pieces of the packed index
+        // stream -- and counts them in shared memory: one private counter array per warp, plain
+        // read-modify-write (the targets of one row are distinct, a warp handles one row at a
+        // time), no atomics of any kind and no global traffic but the index stream itself.
+        extern __shared__ int _b200_tile[];
+        const b200::EventSpaceDev& _es = {{ '_A._es' + get_array_name(pathway.source.variables[pathway.eventspace_name], access_data=False) }};
+        const b200::Slice _mine = b200::owned_cta((int64_t){{b200_counted.size}}, _ctx);
+        const int _T = (int)(_mine.hi - _mine.lo);
+        const int _lane = threadIdx.x & 31, _warp = threadIdx.x >> 5;
+        int* _cnt = _b200_tile + _warp * _pw.tile_stride;
+        for (int _k = _lane; _k < _T; _k += 32) _cnt[_k] = 0;
+        __syncwarp();
+        unsigned long long _nev = 0ULL;
+        const int _segd = _pw.seg_delay;
+        b200::SpikeView _view;
+        _view.total = 0;
+        if (_segd >= 0)
+            _view = b200::view_build(_es, _b200_timestep - _segd, _ctx, false, _A._ctrl);
+        const int _tile = _ctx.gbid;      // tile index = CTA index on this rank
+        for (int _bin = 0; _bin < _pw.nbins; ++_bin)
+        {
+            const int _delay = __ldg(_pw.bin_delay + _bin);
+            const int32_t* _spk = 0;
+            int _n = _view.total;
+            if (_delay != _segd)
+            {
+                _spk = b200::compact_slot(_es, _b200_timestep - _delay);
+                _n = _spk[_es.N];
+            }
+            const int* _tp = _pw.tileptr + (size_t)_bin * (size_t)(_pw.nsrc + 1) * (size_t)(_ctx.gnb + 1) + _tile;
+            // the warp's rows: _s0 + l * kWarps; lane l fetches the descriptor of row l (32
+            // chains of dependent loads in flight), then the rows are walked one after the other
+            // with the index loads of the next row issued ahead of the counting of this one
+            for (int _s0 = _warp; _s0 < _n; _s0 += 32 * b200::kWarps)
+            {
+                const int _s = _s0 + _lane * b200::kWarps;
+                int _beg = 0, _end = 0;
+                if (_s < _n)
+                {
+                    const int _src = (_delay == _segd ? b200::view_id(_view, _s) : _spk[_s]) - _pw.src_start;
+                    if (_src >= 0 && _src < _pw.nsrc)
+                    {
+                        const int* _q = _tp + (size_t)_src * (size_t)(_ctx.gnb + 1);
+                        _beg = __ldg(_q);
+                        _end = __ldg(_q + 1);
+                    }
+                }
+                _nev += (unsigned long long)(_end - _beg);
+                const int _nrows = min(32, (_n - _s0 + b200::kWarps - 1) / b200::kWarps);
+                int _cb = __shfl_sync(0xffffffffu, _beg, 0), _ce = __shfl_sync(0xffffffffu, _end, 0);
+                int _cur[3];
+                #pragma unroll
+                for (int _u = 0; _u < 3; ++_u)
+                    _cur[_u] = (_cb + 32 * _u + _lane < _ce) ? b200::ld_index(_pw.csr_target + _cb + 32 * _u + _lane) : -1;
+                for (int _j = 0; _j < _nrows; ++_j)
+                {
+                    const int _jn = min(_j + 1, 31);
+                    int _nb = __shfl_sync(0xffffffffu, _beg, _jn), _ne = __shfl_sync(0xffffffffu, _end, _jn);
+                    if (_j + 1 >= _nrows) _ne = _nb;
+                    int _nxt[3];
+                    #pragma unroll
+                    for (int _u = 0; _u < 3; ++_u)
+                        _nxt[_u] = (_nb + 32 * _u + _lane < _ne) ? b200::ld_index(_pw.csr_target + _nb + 32 * _u + _lane) : -1;
+                    #pragma unroll
+                    for (int _u = 0; _u < 3; ++_u)
+                    {
+                        if (_cur[_u] >= 0) _cnt[_cur[_u] - (int)_mine.lo] += 1;
+                        __syncwarp();
+                    }
+                    for (int _k = _cb + 96 + _lane; _k - _lane < _ce; _k += 32)     // rows longer than 96 entries
+                    {
+                        if (_k < _ce) _cnt[b200::ld_index(_pw.csr_target + _k) - (int)_mine.lo] += 1;
+                        __syncwarp();
+                    }
+                    _cb = _nb; _ce = _ne;
+                    #pragma unroll
+                    for (int _u = 0; _u < 3; ++_u) _cur[_u] = _nxt[_u];
+                }
+            }
+        }
+        #pragma unroll
+        for (int _o = 16; _o > 0; _o >>= 1) _nev += __shfl_xor_sync(0xffffffffu, _nev, _o);
+        if (_lane == 0 && _nev) atomicAdd(_pw.events, _nev);
+        __syncthreads();
+        for (int _loc = threadIdx.x; _loc < _T; _loc += b200::kBlock)
+        {
+            int _b200_n = 0;
+            #pragma unroll
+            for (int _w = 0; _w < b200::kWarps; ++_w) _b200_n += _b200_tile[_w * _pw.tile_stride + _loc];
+            if (_b200_n == 0) continue;
+            const int _b200_tgt_idx = (int)_mine.lo + _loc;
+            const int _idx = _b200_tgt_idx;
+            const int _vectorisation_idx = _idx;
+            {{b200_apply_loads|autoindent}}
+            for (int _b200_k = 0; _b200_k < _b200_n; ++_b200_k)
+            {
+                {{b200_apply_body|autoindent}}
+            }
+            {{b200_apply_stores|autoindent}}
+        }
+        __syncthreads();
+        return;
+    }
     int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
     B200_FOR_OWNED(_i64, (int64_t){{b200_counted.size}}, _ctx)
     {
@@ -384,7 +493,7 @@ void _run_{{codeobj_name}}_apply()
     _co_{{codeobj_name}}::Scal _sc;
     _hostscal_{{codeobj_name}}(_sc);
     _b200_launch_begin("{{codeobj_name}}");
-    _kernel_{{codeobj_name}}_apply<<<_b200_grid_size(), b200::kBlock, 0, b200::state().stream>>>(_b200_clocks_now(), _sc);
+    _kernel_{{codeobj_name}}_apply<<<_b200_grid_size(), b200::kBlock, _b200_dyn_smem, b200::state().stream>>>(_b200_clocks_now(), _sc);
     _b200_launch_end("{{codeobj_name}}");
 }
 {% endif %}

@@ -51,6 +51,9 @@ _kernel_{{codeobj_name}}(const b200::ConnectArgs _args, const _co_{{codeobj_name
     %CONSTANTS_DEV%
     const int64_t _N_pre = {{constant_or_scalar('N_pre', variables['N_pre'])}};
     const int64_t _N_post = {{constant_or_scalar('N_post', variables['N_post'])}};
+    {% for pointer, start in b200_identity_arrays %}
+    const b200::IdentityIndex {{pointer}}{ {{start}} };   // arange array: the value is the index
+    {% endfor %}
     // scalar code
     {{scalar_code['setup_iterator']|autoindent}}
     {{scalar_code['generator_expr']|autoindent}}

@@ -321,3 +321,71 @@ def test_barrier_plan_of_stdp(brian):
     assert "stdp_S_pre_codeobject" in phases[1] and phases[2][0] == "stdp_S_post_codeobject"
     assert {"stdp_inputs_stateupdater_codeobject", "stdp_neurons_spike_thresholder_codeobject"} <= set(phases[0])
     assert (n, end) == (3, True)
+
+
+def _build_and_dlopen(brian, name, make_network, prefs_update=None):
+    """Generate + cross-compile a project and dlopen the library (RTLD_NOW: every symbol the
+    generated main() calls must be defined -- no compute call is made)."""
+    import models
+
+    b = brian
+    directory = os.path.join(ROOT, "brian2_b200", "_prebuilt", "cpu_" + name)
+    b.device.reinit()
+    b.device.activate()
+    for key, value in (prefs_update or {}).items():
+        b.prefs[key] = value
+    try:
+        b.set_device("b200", directory=directory, build_on_run=False)
+        b.prefs.codegen.cpp.extra_compile_args_gcc = list(models.STRICT_GCC_FLAGS)
+        b.defaultclock.dt = 0.1 * b.ms
+        make_network(b)
+        b.device.build(directory=directory, compile=True, run=False, with_output=False)
+    finally:
+        b.prefs["devices.b200.construction"] = "reference"
+    ctypes.CDLL(os.path.join(directory, "libb200_project.so"), mode=os.RTLD_NOW | os.RTLD_LOCAL)
+    return directory
+
+
+def test_project_with_several_run_calls_links(brian):
+    """Every run() call re-creates its code objects (`..._codeobject_1`): identical sources are
+    compiled once and aliased, including the apply pass of counted pathways."""
+    import models
+
+    def net(b):
+        objs = models.brunel(b, N_E=800, epsilon=0.1, duration=0.0)
+        for _ in range(2):
+            objs["net"].run(0.005 * b.second, namespace={})
+
+    directory = _build_and_dlopen(brian, "two_runs", net)
+    src = open(os.path.join(directory, "b200_kernels.cu")).read()
+    assert "void _run_brunel_exc_pre_codeobject_1_apply() { _run_brunel_exc_pre_codeobject_apply(); }" in src
+    assert "shares its kernels" in src
+
+
+def test_sharded_connect_kernels_compile(brian):
+    """prefs.devices.b200.construction = 'sharded': connect() generator expressions become CUDA
+    kernels (p < 0.25 jump sampling, p >= 0.25, conditions on i/j with subgroup offsets, range
+    generators, one-to-one), and expressions assigned to synaptic variables use the per-synapse
+    host generator."""
+    def net(b):
+        b.seed(3)
+        G = b.NeuronGroup(400, "v : 1", threshold="v > 1", reset="v = 0", name="sc_G")
+        H = b.NeuronGroup(300, "v : 1", name="sc_H")
+        S1 = b.Synapses(G, H, "w : 1", on_pre="v_post += w", name="sc_dense")
+        S1.connect(p=0.4)
+        S1.w = "rand()"
+        S2 = b.Synapses(G[100:300], H[50:250], on_pre="v_post += 1", name="sc_cond")
+        S2.connect(condition="i != j", p=0.1)
+        S3 = b.Synapses(G, H, on_pre="v_post += 1", name="sc_range")
+        S3.connect(j="k for k in range(i % 7, N_post, 7)")
+        b.Network(G, H, S1, S2, S3).run(1 * b.ms, namespace={})
+
+    directory = _build_and_dlopen(brian, "sharded_connect", net,
+                                  prefs_update={"devices.b200.construction": "sharded"})
+    kern = open(os.path.join(directory, "code_objects", "sc_cond_synapses_create_generator_codeobject.cuh")).read()
+    assert "b200::CandidateIter _it;" in kern and "_it.init_sample(" in kern
+    assert "const b200::IdentityIndex _ptr_array_sc_G_i{ 0 };" in kern
+    init = open(os.path.join(directory, "code_objects", "sc_dense_group_variable_set_conditional_codeobject.cpp")).read()
+    assert "b200::SynapseRng _b200_synrng_rand(" in init and "brian::_random_generators" not in init
+    # the reference's host connect is not generated for these objects
+    assert not os.path.exists(os.path.join(directory, "code_objects", "sc_cond_synapses_create_generator_codeobject.cpp"))
