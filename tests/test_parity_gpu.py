@@ -71,6 +71,32 @@ def test_spike_exact_stepwise(brian, project_dir, case):
     brian.prefs["devices.b200.persistent"] = True
 
 
+def test_cobahh_spike_exact_horizon(brian, project_dir):
+    """How long does the Hodgkin-Huxley network stay spike-exact?  The device evaluates exp/expm1
+    with CUDA's algorithms (<= 1-2 ulp from the host's glibc, csrc/b200_functions.cuh), so in a
+    chaotic recurrent network the trains must separate eventually.  Recorded here: one biological
+    second (10 000 steps, 33 948 reference spikes) of COBAHH-1000; the horizon is printed, written
+    to gpurun_out/ and must cover at least the first 100 ms; until the horizon every (i, t) is
+    identical, and over the whole second the population rate agrees within 2 %."""
+    model, kwds = CASES["cobahh_1000_long"]
+    objs, res = models.run_model(brian, model, "b200", project_dir, **kwds)
+    gold = np.load(os.path.join(GOLDEN, "cobahh_1000_long.npz"))
+    gi, gt, ri, rt = gold["spikes_i"], gold["spikes_t"], res["spikes_i"], res["spikes_t"]
+    n = min(len(gi), len(ri))
+    diff = np.nonzero((gi[:n] != ri[:n]) | (gt[:n] != rt[:n]))[0]
+    horizon = float(gt[diff[0]]) if len(diff) else float("inf")
+    identical = int(diff[0]) if len(diff) else n
+    msg = (f"COBAHH-1000: spike trains identical for the first {identical} of {len(gi)} spikes, "
+           f"first difference at t = {horizon * 1e3:.1f} ms")
+    print(msg)
+    out = os.path.join(os.path.dirname(__file__), "..", "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "cobahh_horizon.txt"), "w") as f:
+            f.write(msg + "\n")
+    assert horizon >= 0.1, msg
+    assert abs(len(ri) - len(gi)) <= 0.02 * len(gi), (len(ri), len(gi))
+
+
 def test_in_loop_random_numbers_statistics(brian, project_dir):
     """PoissonInput (binomial sampler) + PoissonGroup on the device's Philox streams: the reference
     disclaims cross-target reproducibility of random numbers (docs_sphinx/advanced/random.rst:28-39),
