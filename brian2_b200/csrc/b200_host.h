@@ -406,6 +406,7 @@ public:
     int hits_n = 0;
     int* d_tileptr = nullptr;      // b200_tiles.cuh
     int tile_stride = 0, tiles_grid = 0;
+    int tile_n = 0;                // size of the target group of a countable pathway (0: not countable)
     bool tiles_tried = false;      // since the CSR was last built
     EventSpace* es = nullptr;
     size_t n_owned = 0;            // synapses stored on this rank (post neuron owned)

@@ -51,7 +51,7 @@ constexpr size_t kTileSmem = (size_t)kWarps * kMaxTile * sizeof(int);
 // Could this pathway be served by tiles on a grid of about `grid_guess` CTAs?  (Decides the
 // dynamic shared memory of the step kernels before the grid size is final.)
 inline bool tiles_candidate(const Pathway& pw, int grid_guess) {
-    if (!pw.prepared || pw.hits_n <= 0 || pw.nbins <= 0 || pw.n_owned == 0) return false;
+    if (!pw.prepared || pw.tile_n <= 0 || pw.nbins <= 0 || pw.n_owned == 0) return false;
     const double nrows = (double)pw.nbins * (double)std::max(1, pw.spikes_stop - pw.spikes_start);
     return (double)pw.n_owned / nrows >= 8.0 * (double)grid_guess;
 }
@@ -68,7 +68,7 @@ inline void tiles_build(Pathway& pw, int grid, size_t dyn_smem) {
     const long long nrows = (long long)pw.nbins * (nsrc + 1) - 0;
     // tile boundaries = the CTAs' blocks of the target group (same arithmetic as owned_cta)
     int64_t lo, hi;
-    EventSpace::rank_range_host(pw.hits_n, st.rank, st.world, lo, hi);
+    EventSpace::rank_range_host(pw.tile_n, st.rank, st.world, lo, hi);
     std::vector<int> start(grid + 1);
     int tmax = 0;
     for (int b = 0; b <= grid; ++b)

@@ -531,28 +531,31 @@ class CUDACodeGenerator(CPPCodeGenerator):
             )
 
             # ---- vector block
-            counted = None
+            counted, dual = None, False
             if self._is_synaptic_effect() and len(ve_block) and prefs["devices.b200.counted_pathways"] != "never":
                 counted = self._countable(ve_block, ve_read, ve_write, ve_indices)
                 if counted is not None and prefs["devices.b200.counted_pathways"] == "auto":
-                    # pure `x_post += constant` scatters are served as well by fp atomics (one phase
-                    # less); counting pays as soon as the code reads target-side data
-                    # (`(unless refractory)` conditions, `v_post += c*(E - v_post)`)
-                    if not (set(ve_read) - set(ve_write)) and all(
-                            s.inplace and s.op in ("+=", "-=") and not (get_identifiers(str(s.expr)) & set(ve_write))
-                            for s in ve_block):
-                        counted = None
+                    # Pure `x_post += constant` scatters: sparse rows are served best by fp
+                    # reductions (one phase less per step), so that stays the delivery -- "dual":
+                    # the counted form is generated next to it and only used when the rows turn
+                    # out to be dense at run time (owner-computes over target tiles).  Code that
+                    # reads target-side data (`(unless refractory)`, `v_post += c*(E - v_post)`)
+                    # is always counted.
+                    dual = not (set(ve_read) - set(ve_write)) and all(
+                        s.inplace and s.op in ("+=", "-=") and not (get_identifiers(str(s.expr)) & set(ve_write))
+                        for s in ve_block)
             if counted is not None:
                 loads, body, stores = self._counted_apply_lines(ve_block, ve_read, ve_write, ve_indices, ve_cond, counted)
                 kwds["b200_apply_loads"] = stripped_deindented_lines("\n".join(loads))
                 kwds["b200_apply_body"] = stripped_deindented_lines("\n".join(body))
                 kwds["b200_apply_stores"] = stripped_deindented_lines("\n".join(stores))
-                ve_code[block_name] = ["atomicAdd(_b200_hits + _b200_tgt_idx, 1);"]
-                self._b200_unroll, self._b200_preloads = 4, []
                 name_of = lambda n: self.device.get_array_name(self.variables[n], access_data=False)
-                access["counted"] = {"size": counted["size"],
+                access["counted"] = {"size": counted["size"], "dual": dual,
                                      "read": sorted(name_of(n) for n in counted["read"]),
                                      "write": sorted(name_of(n) for n in counted["write"])}
+            if counted is not None and not dual:
+                ve_code[block_name] = ["atomicAdd(_b200_hits + _b200_tgt_idx, 1);"]
+                self._b200_unroll, self._b200_preloads = 4, []
                 for name in sc_read | sc_indices:
                     var = self.variables.get(name)
                     if isinstance(var, ArrayVariable):

@@ -157,7 +157,7 @@ prefs.register_preferences(
         """,
     ),
     counted_pathways=BrianPreference(
-        default="always",
+        default="auto",
         docs="""
         Synaptic code that only touches data of the element at the non-source end of a synapse
         (``v_post += J``, with or without ``(unless refractory)``; ``v_post += c*(E - v_post)``)
@@ -166,9 +166,10 @@ prefs.register_preferences(
         apply the statements that many times in the reference's order: bit-identical to the
         sequential reference whatever the constants, several pathways may deliver into one
         variable inside the same phase of a step, and dense rows are accumulated in shared memory.
-        ``'always'``: whenever the code qualifies; ``'auto'``: only when the code reads
-        target-side data (plain ``x_post += constant`` stays a floating-point reduction);
-        ``'never'``.
+        ``'auto'``: code that reads target-side data is counted; plain ``x_post += constant``
+        stays a floating-point reduction while its rows are sparse and switches to the counted
+        owner-computes form when they are dense (decided when the CSR is built);
+        ``'always'``: counted whenever the code qualifies; ``'never'``.
         """,
         validator=lambda v: v in ("always", "auto", "never"),
     ),
@@ -551,7 +552,7 @@ class B200Device(CPPStandaloneDevice):
         if template in ("spikemonitor", "statemonitor", "ratemonitor"):
             for var in self._monitor_buffers(codeobj):
                 shared_w.add(name_of(var))
-        if template == "synapses" and acc.get("counted"):
+        if template == "synapses" and acc.get("counted") and not acc["counted"]["dual"]:
             # the delivery only counts events; the target arrays are touched by the apply pass,
             # element-private (listed here so that they reach the device and come back)
             priv_r |= set(acc["counted"]["read"])
@@ -608,7 +609,7 @@ class B200Device(CPPStandaloneDevice):
                 R += [(E, -1, -1, False), (f"{E}__compact", float("-inf"), -2, False)]
             else:
                 R += [(E, 0, 0, False), (f"{E}__compact", float("-inf"), -1, False)]
-            if acc.get("counted"):
+            if acc.get("counted") and not acc["counted"]["dual"]:
                 # the delivery itself only counts; the target arrays belong to the apply item
                 mine = set(acc["counted"]["read"]) | set(acc["counted"]["write"])
                 R = [r for r in R if r[0] not in mine]
@@ -646,12 +647,14 @@ class B200Device(CPPStandaloneDevice):
         last phase of this one.  Returns (items, end_barrier)."""
         items = []
 
-        def add(name, kind, res, owned, extra=None):
+        def add(name, kind, res, owned, extra=None, exempt=None):
             item = {"name": name, "kind": kind, "res": res, "owned": owned, "share": None,
                     "barrier": False, "phase": 0, "order": len(items)}
             if extra:
                 item.update(extra)
             for other in items:
+                if other is exempt:
+                    continue
                 dep = self._resource_conflict(other["res"], res)
                 if dep == "hard":
                     item["phase"] = max(item["phase"], other["phase"] + 1)
@@ -678,11 +681,22 @@ class B200Device(CPPStandaloneDevice):
                 {"weight": 24 if info["template"] == "synapses" else 1, "variant": variant})
             counted = self._b200_access.get(codeobj.name, {}).get("counted")
             if info["template"] == "synapses" and counted:
-                # the owners of the targets apply the counted events (element-private)
-                hits = f"hits:{info['template_kwds']['pathway'].name}"
-                R = [(n, *self._ALWAYS, True) for n in counted["read"]] + [(hits, 0, 0, False)]
+                # the owners of the targets apply the counted events (element-private); with
+                # dense rows they also do the counting, straight from the spike lists
+                delivery = items[-1]
+                E = self.get_array_name(info["template_kwds"]["pathway"].source.variables[
+                    info["template_kwds"]["pathway"].eventspace_name], access_data=False)
+                lists = [r for r in res[0] if r[0] in (E, f"{E}__compact")]
+                R = [(n, *self._ALWAYS, True) for n in counted["read"]] + lists
                 W = [(n, *self._ALWAYS, True) for n in counted["write"]]
-                add(codeobj.name, "apply", (R, W), True, {"variant": variant})
+                if counted["dual"]:
+                    # either the delivery (sparse rows: fp reductions) or the apply pass (dense
+                    # rows) does the work of this pathway, never both: no ordering between them
+                    add(codeobj.name, "apply", (R, W), True, {"variant": variant}, exempt=delivery)
+                    items[-1]["phase"] = max(items[-1]["phase"], delivery["phase"])
+                else:
+                    R.append((f"hits:{info['template_kwds']['pathway'].name}", 0, 0, False))
+                    add(codeobj.name, "apply", (R, W), True, {"variant": variant})
         items.sort(key=lambda it: (it["phase"], it["order"]))
         last = -1
         for it in items:
@@ -929,14 +943,15 @@ class B200Device(CPPStandaloneDevice):
         out = []
         for S in sorted(synapses, key=lambda s: s.name):
             for path in sorted(S._pathways, key=lambda p: p.name):
-                hits_n = 0
+                hits_n = tile_n = 0
                 for codeobj in self.code_objects.values():
                     info = self._b200_info.get(codeobj.name)
                     if info is not None and info["template"] == "synapses" \
                             and info["template_kwds"]["pathway"].name == path.name:
                         counted = self._b200_access.get(codeobj.name, {}).get("counted")
                         if counted:
-                            hits_n = int(counted["size"])
+                            tile_n = int(counted["size"])
+                            hits_n = 0 if counted["dual"] else tile_n
                 out.append(
                     {
                         "name": path.name,
@@ -944,6 +959,7 @@ class B200Device(CPPStandaloneDevice):
                         "start": int(path.source.start),
                         "stop": int(path.source.stop),
                         "hits_n": hits_n,
+                        "tile_n": tile_n,
                     }
                 )
         return out

@@ -94,7 +94,8 @@ void _b200_tiles_reserve()
 {
     bool any = false;
     {% for pw in b200_pathways %}
-    {% if pw.hits_n %}
+    {% if pw.tile_n %}
+    brian::{{pw.name}}.tile_n = {{pw.tile_n}};
     any = any || b200::tiles_candidate(brian::{{pw.name}}, 2 * b200::state().num_sms);
     {% endif %}
     {% endfor %}
@@ -105,7 +106,7 @@ void _b200_tiles_build()
     const int grid = _b200_grid_size();
     (void)grid;
     {% for pw in b200_pathways %}
-    {% if pw.hits_n %}
+    {% if pw.tile_n %}
     if (brian::{{pw.name}}.prepared && (!brian::{{pw.name}}.tiles_tried || brian::{{pw.name}}.tiles_grid != grid)) {
         b200::tiles_build(brian::{{pw.name}}, grid, (size_t)_b200_dyn_smem);
         brian::{{pw.name}}.tiles_tried = true;

@@ -46,9 +46,11 @@
     }
     {% else %}
     {% if b200_counted %}
+    {% if not b200_counted.dual %}
     // counted pathway: the delivery only counts the events per target (integer reductions);
     // the owner of every target applies them afterwards (_dev_{{codeobj_name}}_apply below)
     int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    {% endif %}
     if (_pw.tileptr) return;    // dense rows: counted AND applied by the owners of the targets (apply pass)
     {% endif %}
     const int _lane = threadIdx.x & 31;
@@ -406,35 +408,56 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
                     }
                 }
                 _nev += (unsigned long long)(_end - _beg);
+                // rows are walked in groups of 4; the index loads of the next group (up to 3 lines
+                // of 32 entries per row) are issued before the entries of this group are counted
                 const int _nrows = min(32, (_n - _s0 + b200::kWarps - 1) / b200::kWarps);
-                int _cb = __shfl_sync(0xffffffffu, _beg, 0), _ce = __shfl_sync(0xffffffffu, _end, 0);
-                int _cur[3];
+                int _cur[4][3];
                 #pragma unroll
-                for (int _u = 0; _u < 3; ++_u)
-                    _cur[_u] = (_cb + 32 * _u + _lane < _ce) ? b200::ld_index(_pw.csr_target + _cb + 32 * _u + _lane) : -1;
-                for (int _j = 0; _j < _nrows; ++_j)
+                for (int _r = 0; _r < 4; ++_r)
                 {
-                    const int _jn = min(_j + 1, 31);
-                    int _nb = __shfl_sync(0xffffffffu, _beg, _jn), _ne = __shfl_sync(0xffffffffu, _end, _jn);
-                    if (_j + 1 >= _nrows) _ne = _nb;
-                    int _nxt[3];
+                    const int _b = __shfl_sync(0xffffffffu, _beg, _r);
+                    const int _e = _r < _nrows ? __shfl_sync(0xffffffffu, _end, _r) : _b;
                     #pragma unroll
                     for (int _u = 0; _u < 3; ++_u)
-                        _nxt[_u] = (_nb + 32 * _u + _lane < _ne) ? b200::ld_index(_pw.csr_target + _nb + 32 * _u + _lane) : -1;
+                        _cur[_r][_u] = (_b + 32 * _u + _lane < _e) ? b200::ld_index(_pw.csr_target + _b + 32 * _u + _lane) : -1;
+                }
+                for (int _j = 0; _j < _nrows; _j += 4)
+                {
+                    int _nxt[4][3];
                     #pragma unroll
-                    for (int _u = 0; _u < 3; ++_u)
+                    for (int _r = 0; _r < 4; ++_r)
                     {
-                        if (_cur[_u] >= 0) _cnt[_cur[_u] - (int)_mine.lo] += 1;
-                        __syncwarp();
+                        const int _jn = _j + 4 + _r;
+                        const int _b = __shfl_sync(0xffffffffu, _beg, _jn & 31);
+                        const int _e = _jn < _nrows ? __shfl_sync(0xffffffffu, _end, _jn & 31) : _b;
+                        #pragma unroll
+                        for (int _u = 0; _u < 3; ++_u)
+                            _nxt[_r][_u] = (_b + 32 * _u + _lane < _e) ? b200::ld_index(_pw.csr_target + _b + 32 * _u + _lane) : -1;
                     }
-                    for (int _k = _cb + 96 + _lane; _k - _lane < _ce; _k += 32)     // rows longer than 96 entries
-                    {
-                        if (_k < _ce) _cnt[b200::ld_index(_pw.csr_target + _k) - (int)_mine.lo] += 1;
-                        __syncwarp();
-                    }
-                    _cb = _nb; _ce = _ne;
                     #pragma unroll
-                    for (int _u = 0; _u < 3; ++_u) _cur[_u] = _nxt[_u];
+                    for (int _r = 0; _r < 4; ++_r)
+                    {
+                        #pragma unroll
+                        for (int _u = 0; _u < 3; ++_u)
+                        {
+                            if (_cur[_r][_u] >= 0) _cnt[_cur[_r][_u] - (int)_mine.lo] += 1;
+                            __syncwarp();
+                        }
+                        // rows with more than 96 entries in this tile: the rest, line by line
+                        const int _b = __shfl_sync(0xffffffffu, _beg, (_j + _r) & 31);
+                        const int _e = _j + _r < _nrows ? __shfl_sync(0xffffffffu, _end, (_j + _r) & 31) : _b;
+                        for (int _k = _b + 96 + _lane; _k - _lane < _e; _k += 32)
+                        {
+                            if (_k < _e) _cnt[b200::ld_index(_pw.csr_target + _k) - (int)_mine.lo] += 1;
+                            __syncwarp();
+                        }
+                    }
+                    #pragma unroll
+                    for (int _r = 0; _r < 4; ++_r)
+                    {
+                        #pragma unroll
+                        for (int _u = 0; _u < 3; ++_u) _cur[_r][_u] = _nxt[_r][_u];
+                    }
                 }
             }
         }
@@ -461,6 +484,9 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
         __syncthreads();
         return;
     }
+    {% if b200_counted.dual %}
+    // (sparse rows of this pathway are delivered by floating-point reductions: nothing to apply)
+    {% else %}
     int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
     B200_FOR_OWNED(_i64, (int64_t){{b200_counted.size}}, _ctx)
     {
@@ -477,6 +503,7 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
         }
         {{b200_apply_stores|autoindent}}
     }
+    {% endif %}
 }
 
 __global__ void __launch_bounds__(b200::kBlock, {{prefs.devices.b200.ctas_per_sm}})

@@ -62,7 +62,9 @@ def _schedules(src):
         if tag in out:
             continue
         end = sched.rstrip().endswith("|")
-        phases = [p.split() for p in sched.rstrip().rstrip("|").split("|")]
+        # (a model built twice in one process gets `_1`-suffixed code object names)
+        phases = [[re.sub(r"_codeobject_\d+", "_codeobject", w) for w in p.split()]
+                  for p in sched.rstrip().rstrip("|").split("|")]
         n = int(re.search(rf"//   \[{tag}\] grid barriers per step: (\d+)", src).group(1))
         out[tag] = (phases, n, end)
     return out
@@ -71,35 +73,49 @@ def _schedules(src):
 def test_barrier_plan_of_cuba(cuba_project):
     """Phases of a CUBA step.  stateupdate -> threshold -> reset share the owned partition (no
     barrier: the resetter only touches the CTA's own segment); one barrier before the consumers
-    of the spike list (monitor, the two counted deliveries, compaction); one before the owners
-    apply the counted events; NO barrier at the end of the step (the next state update only
-    meets element-private data).  With delays >= 1 step ('d1') the deliveries move in front of
-    the first barrier and one barrier per step is left."""
+    of the spike list (monitor, the two deliveries, compaction); one at the end of the step (the
+    deliveries accumulate `ge`/`gi` with reductions, the next state update reads them).  The
+    apply passes of the two "dual" pathways sit next to their deliveries: they only do
+    something when the rows are dense (owner-computes over target tiles)."""
     plans = _schedules(open(os.path.join(cuba_project, "b200_kernels.cu")).read())
+    assert list(plans) == ["d0"]          # delays make no difference to this schedule
     phases, n, end = plans["d0"]
     assert phases == [
         ["cuba_P_stateupdater_codeobject", "cuba_P_spike_thresholder_codeobject", "cuba_P_spike_resetter_codeobject"],
-        ["cuba_spikes_codeobject", "cuba_Ce_pre_codeobject", "cuba_Ci_pre_codeobject",
-         "compact_array_cuba_P__spikespace"],
-        ["cuba_Ce_pre_codeobject@apply", "cuba_Ci_pre_codeobject@apply"]], phases
-    assert (n, end) == (2, False)
-    phases, n, end = plans["d1"]
-    assert phases[0][:4] == ["cuba_P_stateupdater_codeobject", "cuba_P_spike_thresholder_codeobject",
-                             "cuba_Ce_pre_codeobject", "cuba_Ci_pre_codeobject"], phases
-    assert (len(phases), n, end) == (2, 1, False)
+        ["cuba_spikes_codeobject", "cuba_Ce_pre_codeobject", "cuba_Ce_pre_codeobject@apply",
+         "cuba_Ci_pre_codeobject", "cuba_Ci_pre_codeobject@apply", "compact_array_cuba_P__spikespace"]], phases
+    assert (n, end) == (2, True)
 
 
-def test_constant_synaptic_effect_is_counted_not_accumulated_in_floating_point(cuba_project):
-    """`ge_post += we` touches target-side data only: the delivery counts events per target with
-    integer reductions and the owner of the target applies `ge += we` that many times -- the
-    reference's sequential read-modify-write survives only inside that element-private loop."""
+def test_synaptic_effect_uses_reductions_not_rmw(cuba_project):
+    """`ge_post += we`: the delivery issues reductions (the reference's sequential
+    read-modify-write must not survive in the scattered code); the same statement survives, as a
+    plain loop, only in the element-private apply pass used for dense rows."""
     code = open(os.path.join(cuba_project, "code_objects", "cuba_Ce_pre_codeobject.cuh")).read()
     deliver = code.split("__device__ __forceinline__ void _dev_cuba_Ce_pre_codeobject(")[1].split("__global__")[0]
-    assert "atomicAdd(_b200_hits + _b200_tgt_idx, 1);" in deliver
-    assert "_ptr_array_cuba_P_ge[" not in deliver.split("// scalar code")[1]
+    assert "b200::atomic_add(&_ptr_array_cuba_P_ge[_postsynaptic_idx]" in deliver
+    assert "ge[_postsynaptic_idx] = ge" not in deliver.replace("_ptr_array_cuba_P_", "")
+    assert "if (_pw.tileptr) return;" in deliver
     apply = code.split("void _dev_cuba_Ce_pre_codeobject_apply(")[1].split("__global__")[0]
+    assert "extern __shared__ int _b200_tile[];" in apply
     assert "for (int _b200_k = 0; _b200_k < _b200_n; ++_b200_k)" in apply
-    assert "ge += we;" in apply and "_ptr_array_cuba_P_ge[_postsynaptic_idx] = ge;" in apply
+    assert "ge += we;" in apply and "_b200_hits" not in apply
+
+
+def test_counted_pathway_code_of_brunel(brian):
+    """`v_post += J` with `v` declared `(unless refractory)` reads target-side state: the delivery
+    counts events per target with integer reductions (no gather of `not_refractory` per event)
+    and the owner applies `if(not_refractory) v += J` once per counted event."""
+    import __graft_entry__ as ge
+
+    directory, _ = ge.build_project("brunel_hetero", directory=os.path.join(ge.PREBUILT, "cpu_brunel_hetero"))
+    code = open(os.path.join(directory, "code_objects", "brunel_exc_pre_codeobject.cuh")).read()
+    deliver = code.split("__device__ __forceinline__ void _dev_brunel_exc_pre_codeobject(")[1].split("__global__")[0]
+    assert "atomicAdd(_b200_hits + _b200_tgt_idx, 1);" in deliver
+    assert "not_refractory" not in deliver.split("// scalar code")[1]
+    apply = code.split("void _dev_brunel_exc_pre_codeobject_apply(")[1].split("__global__")[0]
+    assert "const int _b200_n = __ldcg(_b200_hits + _b200_tgt_idx);" in apply
+    assert "if(not_refractory)" in apply and "v += J;" in apply
 
 
 def test_no_cpu_fallback_without_gpu(cuba_project):
@@ -358,7 +374,8 @@ def test_project_with_several_run_calls_links(brian):
 
     directory = _build_and_dlopen(brian, "two_runs", net)
     src = open(os.path.join(directory, "b200_kernels.cu")).read()
-    assert "void _run_brunel_exc_pre_codeobject_1_apply() { _run_brunel_exc_pre_codeobject_apply(); }" in src
+    assert re.search(r"void _run_brunel_exc_pre_codeobject_\d+_apply\(\) "
+                     r"\{ _run_brunel_exc_pre_codeobject(_\d+)?_apply\(\); \}", src)
     assert "shares its kernels" in src
 
 
