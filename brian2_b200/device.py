@@ -692,7 +692,9 @@ class B200Device(CPPStandaloneDevice):
                 if counted["dual"]:
                     # either the delivery (sparse rows: fp reductions) or the apply pass (dense
                     # rows) does the work of this pathway, never both: no ordering between them
-                    add(codeobj.name, "apply", (R, W), True, {"variant": variant}, exempt=delivery)
+                    add(codeobj.name, "apply", (R, W), True,
+                        {"variant": variant, "dual": True, "pathway": info["template_kwds"]["pathway"].name},
+                        exempt=delivery)
                     items[-1]["phase"] = max(items[-1]["phase"], delivery["phase"])
                 else:
                     R.append((f"hits:{info['template_kwds']['pathway'].name}", 0, 0, False))

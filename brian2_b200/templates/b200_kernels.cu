@@ -191,6 +191,7 @@ _b200_persistent_{{plan.index}}_{{v.tag}}(const _B200Clocks _clks0, const long l
         {% if item.barrier %}
         _stop |= b200::grid_barrier(&_A._ctrl->barrier, _bar_target, _ctx);
         B200_PHASE({{2 * loop.index0}})
+        {% elif item.kind == 'apply' and item.dual %}
         {% elif not loop.first %}
         __syncthreads();
         {% endif %}
@@ -212,6 +213,9 @@ _b200_persistent_{{plan.index}}_{{v.tag}}(const _B200Clocks _clks0, const long l
         }
         {% elif item.kind == 'compact' %}
         b200::compact_segments(_A._es{{item.es}}, _clks.{{item.clock}}.timestep, _ctx, _A._ctrl);
+        {% elif item.kind == 'apply' and item.dual %}
+        if (_A._pw_{{item.pathway}}.tileptr)       // dense rows only (sparse rows: delivered by reductions)
+            _dev_{{item.name}}_apply(_ctx, _clks, _sc.{{item.name}});
         {% elif item.kind == 'apply' %}
         _dev_{{item.name}}_apply(_ctx, _clks, _sc.{{item.name}});
         {% else %}
