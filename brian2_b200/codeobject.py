@@ -152,6 +152,14 @@ DEFAULT_FUNCTIONS["randn"].implementations.add_implementation(
 )
 
 
+# poisson(lam): the reference's samplers on the element's Philox stream (b200::rng_poisson)
+DEFAULT_FUNCTIONS["poisson"].implementations.add_implementation(
+    B200CodeObject,
+    code={"support_code": "", "hashdefine_code": "#define _poisson(_lam, _i) b200::rng_poisson(_rng, (_lam))"},
+    name="_poisson",
+)
+
+
 def _synapses_of(owner):
     """The `Synapses` object behind ``owner`` (itself, or the owner of a `SynapticPathway`)."""
     return getattr(owner, "synapses", owner)

@@ -641,5 +641,55 @@ __device__ __forceinline__ double rng_normal(Rng& r) {
     return f * x2;
 }
 
+// ---------------------------------------------------------------------------------------------
+// poisson(lam) for in-loop code: the reference's two samplers (cpp_generator.py:661-751, the
+// legacy numpy algorithms) on the element's Philox stream.  lam < 10: multiply uniforms until
+// the product drops below exp(-lam); lam >= 10: Hoermann's transformed rejection with squeeze
+// (PTRS), with the log-gamma of its acceptance test from the Stirling series after shifting the
+// argument above 7.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_gamma_stirling(double x) {
+    if (x == 1.0 || x == 2.0) return 0.0;
+    const double c[10] = {8.333333333333333e-02, -2.777777777777778e-03, 7.936507936507937e-04,
+                          -5.952380952380952e-04, 8.417508417508418e-04, -1.917526917526918e-03,
+                          6.410256410256410e-03, -2.955065359477124e-02, 1.796443723688307e-01,
+                          -1.39243221690590e+00};
+    int shift = 0;
+    double y = x;
+    if (x <= 7.0) { shift = (int)(7.0 - x); y = x + shift; }
+    const double inv2 = 1.0 / (y * y);
+    double series = c[9];
+#pragma unroll
+    for (int k = 8; k >= 0; --k) series = series * inv2 + c[k];
+    double lg = series / y + 0.5 * log(6.283185307179586) + (y - 0.5) * log(y) - y;
+    for (int k = 0; k < shift; ++k) { y -= 1.0; lg -= log(y); }
+    return lg;
+}
+
+__device__ __forceinline__ int32_t rng_poisson(Rng& r, double lam) {
+    if (lam == 0.0) return 0;
+    if (lam < 10.0) {
+        const double floor_ = exp(-lam);
+        int32_t n = 0;
+        double prod = rng_uniform(r);
+        while (prod > floor_) { ++n; prod *= rng_uniform(r); }
+        return n;
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double v_r = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double u = rng_uniform(r) - 0.5;
+        const double v = rng_uniform(r);
+        const double us = 0.5 - fabs(u);
+        const int32_t k = (int32_t)floor((2.0 * a / us + b) * u + lam + 0.43);
+        if (us >= 0.07 && v <= v_r) return k;
+        if (k < 0 || (us < 0.013 && v > us)) continue;
+        if (log(v) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - log_gamma_stirling(k + 1.0))
+            return k;
+    }
+}
 
 }  // namespace b200

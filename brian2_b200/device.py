@@ -698,7 +698,8 @@ class B200Device(CPPStandaloneDevice):
                     items[-1]["phase"] = max(items[-1]["phase"], delivery["phase"])
                 else:
                     R.append((f"hits:{info['template_kwds']['pathway'].name}", 0, 0, False))
-                    add(codeobj.name, "apply", (R, W), True, {"variant": variant})
+                    add(codeobj.name, "apply", (R, W), True,
+                        {"variant": variant, "dual": False, "pathway": info["template_kwds"]["pathway"].name})
         items.sort(key=lambda it: (it["phase"], it["order"]))
         last = -1
         for it in items:
