@@ -30,7 +30,7 @@ from brian2.codegen.permutation_analysis import (
     check_for_order_independence,
 )
 from brian2.codegen.statements import Statement
-from brian2.core.clocks import Clock
+from brian2.core.clocks import BaseClock, Clock  # noqa: F401
 from brian2.core.preferences import prefs
 from brian2.parsing.rendering import CPPNodeRenderer
 from brian2.core.functions import Function
@@ -67,7 +67,8 @@ def clock_field(var):
     """If ``var`` is the ``t``/``dt``/``timestep`` array of a `Clock`, return the field name."""
     owner = getattr(var, "owner", None)
     try:
-        if isinstance(owner, Clock) and var.name in ("t", "dt", "timestep") and isinstance(var, ArrayVariable):
+        # (EventClock -- arbitrary sample times -- is a sibling of Clock: both derive from BaseClock)
+        if isinstance(owner, BaseClock) and var.name in ("t", "dt", "timestep") and isinstance(var, ArrayVariable):
             return var.name
     except ReferenceError:
         pass
@@ -311,13 +312,22 @@ class CUDACodeGenerator(CPPCodeGenerator):
         """Return (hoisted [(ctype, name)], host_lines, dev_lines) for one scalar block."""
         known = {}
         hoisted, host_lines, dev_lines = [], [], []
+        self._b200_scalar_write_lines = []
+        written = set()
         for stmt in statements:
-            if stmt.op != ":=":
-                raise NotImplementedError(
-                    "b200 device: writes to shared (scalar) variables inside the simulation loop "
-                    f"are not supported yet (statement '{stmt.var} {stmt.op} ...')"
-                )
             ids = get_identifiers(str(stmt.expr))
+            if stmt.op != ":=":
+                # write to a shared (scalar) variable (`run_regularly('total += 1')`,
+                # stateupdate.cpp: ALLOWS_SCALAR_WRITE): executed by ONE thread of the grid
+                # after everybody's temporaries (see translate_statement_sequence)
+                written.add(stmt.var)
+                self._b200_scalar_write_lines.append(self.translate_statement(stmt))
+                continue
+            if ids & written:
+                raise NotImplementedError(
+                    "b200 device: a loop-invariant temporary that depends on a shared variable written "
+                    f"by the same code ('{stmt.var} := {stmt.expr}')"
+                )
             inv = all(self._invariant_name(i, known) for i in ids)
             known[stmt.var] = inv
             line = self.translate_statement(stmt)
@@ -482,15 +492,19 @@ class CUDACodeGenerator(CPPCodeGenerator):
                     keep_exp_pow=bool(prefs["devices.b200.fuse_exp_pow"]),
                 ).run(ve_block)
             sc_read, sc_write, sc_indices, sc_cond = self.arrays_helper(sc_block)
-            if sc_write:
-                # (stateupdate.cpp is ALLOWS_SCALAR_WRITE: e.g. `run_regularly('shared_var = ...')`.
-                # On the device every thread evaluates the scalar block, so a shared variable
-                # that is read and written there would need two grid barriers per step.)
-                raise NotImplementedError(
-                    "b200 device: code that writes to shared (scalar) variables inside the simulation "
-                    f"loop ({', '.join(sorted(sc_write))} in '{self.name}')"
-                )
             ve_read, ve_write, ve_indices, ve_cond = self.arrays_helper(ve_block)
+            if sc_write:
+                # stateupdate.cpp is ALLOWS_SCALAR_WRITE (`run_regularly('shared_var += ...')`).  Every
+                # thread evaluates the scalar block, so the write itself is done by one elected
+                # thread; the per-element code of the SAME code object must not read the variable
+                # (it could see either value) -- other code objects are ordered by grid barriers
+                # (the barrier analysis sees a shared write).
+                clash = sorted(set(sc_write) & (set(ve_read) | set(ve_write)))
+                if clash or any(c is not None for c in sc_cond.values()):
+                    raise NotImplementedError(
+                        "b200 device: per-element code that reads a shared (scalar) variable written "
+                        f"by the same code object ({', '.join(clash)} in '{self.name}')"
+                    )
             if self.template_name == "synapses_create_generator":
                 # the device version of connect() evaluates index arithmetic and rand() only;
                 # conditions that read state variables of the connected groups need the
@@ -521,7 +535,14 @@ class CUDACodeGenerator(CPPCodeGenerator):
 
             # ---- scalar block
             read_lines = self.translate_to_read_arrays(sc_read, sc_write, sc_indices)
+            if sc_write:
+                read_lines += self.translate_to_declarations(sc_read, sc_write, sc_indices)
             hoisted, host_lines, dev_lines = self._split_scalar_block(sc_block, sc_read)
+            if sc_write:
+                dev_lines += (["if (_ctx.gbid == 0 && threadIdx.x == 0)", "{"]
+                              + ["    " + ln for ln in self._b200_scalar_write_lines]
+                              + ["    " + ln for ln in self.translate_to_write_arrays(sc_write)]
+                              + ["}"])
             sc_code[block_name] = stripped_deindented_lines("\n".join(read_lines + dev_lines))
             scal_members[block_name] = hoisted
             fill = [f"_sc.{name} = {name};" for _, name in hoisted]
@@ -589,6 +610,10 @@ class CUDACodeGenerator(CPPCodeGenerator):
                 var = self.variables.get(name)
                 if isinstance(var, ArrayVariable):
                     key = "write" if self.variable_indices[name] in ("_idx", "0") else "scattered_write"
+                    if name in sc_write:     # one thread writes what every thread of the grid may read
+                        key = "scattered_write"
+                        access.setdefault("scalar_write", set()).add(
+                            self.device.get_array_name(var, access_data=False))
                     access[key].add(self.device.get_array_name(var, access_data=False))
 
         if set(scal_host.keys()) == {None}:

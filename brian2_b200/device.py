@@ -593,6 +593,12 @@ class B200Device(CPPStandaloneDevice):
         elif template == "ratemonitor":
             es = codeobj.variables["_spikespace"]
         E = name_of(es) if es is not None else None
+        # shared (scalar) variables that some in-loop code writes are nobody's private data
+        shared_scalars = set()
+        for a in self._b200_access.values():
+            shared_scalars |= set(a.get("scalar_write", ()))
+        R = [(n, lo, hi, p and n not in shared_scalars) for (n, lo, hi, p) in R]
+        W = [(n, lo, hi, p and n not in shared_scalars) for (n, lo, hi, p) in W]
         # the event-space entries of _codeobj_access are replaced by step-resolved ones
         R = [r for r in R if r[0] not in (E, f"{E}__compact")]
         W = [w for w in W if w[0] != E]
@@ -939,7 +945,10 @@ class B200Device(CPPStandaloneDevice):
         for codeobj in self.code_objects.values():
             info = self._b200_info.get(codeobj.name)
             if info is not None and info["template"] == "summed_variable":
-                names.add(f'{info["owner"].name}_{info["template_kwds"]["_target_var"].name}')
+                # (one index per summed variable: a Synapses object may define `x_pre` and `x_post`
+                # sums of equally named variables of two groups)
+                target = self.get_array_name(info["template_kwds"]["_target_var"], access_data=False)
+                names.add(f'{info["owner"].name}{target}')
         return sorted(names)
 
     def _pathways(self, synapses):

@@ -57,6 +57,11 @@ B200_REGISTER_KERNEL(_kernel_{{codeobj_name}})
 
 void _run_{{codeobj_name}}()
 {
+    // Called from main() outside of a Network::run (e.g. StateMonitor.record_single_timestep(),
+    // monitors/statemonitor.py:398-420): the host mirrors are the truth between runs, so the
+    // single launch is bracketed by the same upload / download as a run.
+    const bool _standalone_call = !Network::_globally_running;
+    if (_standalone_call) { _b200_upload(); _b200_prepare_steps(1, true); }
     _co_{{codeobj_name}}::Scal _sc;
     _hostscal_{{codeobj_name}}(_sc);
     {% block host_prelaunch %}
@@ -66,6 +71,7 @@ void _run_{{codeobj_name}}()
     {% block host_postlaunch %}
     {% endblock %}
     _b200_launch_end("{{codeobj_name}}");
+    if (_standalone_call) { B200_CUDA(cudaStreamSynchronize(b200::state().stream)); _b200_download(); }
 }
 {% block extra_device_code %}
 {% endblock %}

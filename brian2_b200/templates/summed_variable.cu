@@ -8,7 +8,7 @@
 {% extends 'common_group.cu' %}
 {% block maincode %}
     {% set _target_var_array = get_array_name(_target_var) %}
-    const b200::TargetIndexDev& _ti = _A._sv_{{owner.name}}_{{_target_var.name}};
+    const b200::TargetIndexDev& _ti = _A._sv_{{owner.name}}{{get_array_name(_target_var, access_data=False)}};
     // scalar code
     {{scalar_code|autoindent}}
     {% if b200_target_whole_group %}
@@ -41,7 +41,7 @@
     {
         std::vector<int32_t>& _b200_index = {{_index_array}};
         const int _target_size = {{b200_host_constant_or_scalar(_target_size_name, variables[_target_size_name])}};
-        _b200_sv_{{owner.name}}_{{_target_var.name}}.prepare(_b200_index.empty() ? 0 : &_b200_index[0], _b200_index.size(),
+        _b200_sv_{{owner.name}}{{get_array_name(_target_var, access_data=False)}}.prepare(_b200_index.empty() ? 0 : &_b200_index[0], _b200_index.size(),
                                        {{_target_start}}, _target_size);
     }
 {% endblock %}

@@ -54,11 +54,17 @@ CASES = {
     "timedarray": ("timedarray", dict(N=100, duration=0.05)),
     # stochastic (in-loop RNG): the golden file holds the reference's statistics only
     "poisson_drive": ("poisson_drive", dict(N=2000, duration=0.1)),
+    "poissonfn": ("poissonfn", dict(N=4000, duration=0.02)),
+    # several clocks + scalar writes, shared variable on the main clock,
+    # clock-driven synaptic equations + summed variable
+    "multiclock": ("multiclock", dict(N=200, duration=0.05)),
+    "sharedvar": ("sharedvar", dict(N=300, duration=0.03)),
+    "synstate": ("synstate", dict(N=150, duration=0.03)),
 }
 
 
 #: cases that draw random numbers inside the time loop (compared statistically)
-STOCHASTIC = {"poisson_drive"}
+STOCHASTIC = {"poisson_drive", "poissonfn"}
 
 
 def main(argv):

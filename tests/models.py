@@ -449,6 +449,95 @@ def submon(b, N=600, duration=0.05, seed=77):
 MODELS["submon"] = submon
 
 
+def multiclock(b, N=200, duration=0.05, seed=41):
+    """Several clocks in one network (network.cpp:134-159 `next_clocks`): neurons on the default
+    clock (0.1 ms), a `run_regularly` that writes a SHARED variable every 1 ms (stateupdate.cpp:
+    ALLOWS_SCALAR_WRITE), a StateMonitor every 0.5 ms, a rate monitor.  The drive only takes
+    dyadic values, so every product in the update is exact and the states are bit-comparable."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """dv/dt = (drive - v)/(8*ms) : 1
+                            drive : 1 (shared)
+                            ticks : 1 (shared)""", threshold="v > 1", reset="v = 0", method="euler",
+                      name="mc_neurons")
+    G.v = "rand()"
+    G.drive = 1.5
+    G.run_regularly("drive = 1.25 + 0.25*(int(ticks) % 4)\nticks += 1", dt=1 * ms, name="mc_drive")
+    objs = dict(G=G)
+    objs["spikes"] = b.SpikeMonitor(G, name="mc_spikes")
+    objs["trace"] = b.StateMonitor(G, ["v", "drive"], record=[0, 7, N - 1], dt=0.5 * ms, name="mc_trace")
+    objs["rate"] = b.PopulationRateMonitor(G, name="mc_rate")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("G", "drive"), ("G", "ticks")]
+    return objs
+
+
+def sharedvar(b, N=300, duration=0.03, seed=43):
+    """A shared variable written inside the loop on the SAME clock as everything else (persistent
+    kernel: the writer is one elected thread, readers are ordered by grid barriers): a counter
+    driven `run_regularly`, read by the state updater and by synaptic code."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """dv/dt = (gain - v)/(5*ms) : 1
+                            gain : 1 (shared)
+                            n_steps : 1 (shared)
+                            x : 1""", threshold="v > 1", reset="v = 0", method="euler", name="sv_neurons")
+    G.v = "rand()"
+    G.gain = 1.5
+    G.run_regularly("n_steps += 1\ngain = 1.25 + 0.125*(int(n_steps) % 5)", when="start", name="sv_rr")
+    S = b.Synapses(G, G, on_pre="x_post += gain_pre", name="sv_S")
+    S.connect(p=0.05)
+    objs = dict(G=G, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="sv_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("G", "x"), ("G", "gain"), ("G", "n_steps")]
+    return objs
+
+
+def synstate(b, N=150, duration=0.03, seed=47):
+    """Clock-driven synaptic state (stateupdate.cpp with N = number of synapses, `constant_or_scalar('N')`):
+    a per-synapse conductance `g` decays every step, jumps on presynaptic spikes and drives the
+    postsynaptic neuron through a summed variable (summed_variable.cpp)."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """dv/dt = (1.1 - v + I)/(10*ms) : 1
+                            I : 1""", threshold="v > 1", reset="v = 0", method="euler", name="sy_neurons")
+    G.v = "rand()"
+    S = b.Synapses(G, G, """dg/dt = -g/(4*ms) : 1 (clock-driven)
+                            I_post = 0.05*g : 1 (summed)""", on_pre="g += 1", method="euler", name="sy_S")
+    S.connect(condition="i != j", p=0.1)
+    S.g = "rand()"
+    objs = dict(G=G, S=S)
+    objs["spikes"] = b.SpikeMonitor(G, name="sy_spikes")
+    objs["net"] = b.Network(*objs.values())
+    objs["duration"] = duration
+    objs["state"] = [("G", "v"), ("G", "I"), ("S", "g")]
+    return objs
+
+
+def poissonfn(b, N=4000, duration=0.02, seed=53):
+    """`poisson(lam)` inside the loop (cpp_generator.py:661-751: multiplication sampler for lam < 10,
+    PTRS for lam >= 10) -- statistical comparison only."""
+    b.seed(seed)
+    ms = b.ms
+    G = b.NeuronGroup(N, """small : 1
+                            large : 1
+                            acc_small : 1
+                            acc_large : 1""", name="pf_neurons")
+    G.run_regularly("small = poisson(2.5)\nlarge = poisson(40.0)\nacc_small += small\nacc_large += large",
+                    name="pf_rr")
+    objs = dict(G=G)
+    objs["net"] = b.Network(G)
+    objs["duration"] = duration
+    objs["state"] = [("G", "acc_small"), ("G", "acc_large"), ("G", "small"), ("G", "large")]
+    return objs
+
+
+MODELS.update(multiclock=multiclock, sharedvar=sharedvar, synstate=synstate, poissonfn=poissonfn)
+
+
 def run_model(b, name, device_name, directory, build_kwds=None, prefs_update=None, n_runs=1, **model_kwds):
     """Build + run ``name`` on ``device_name``; returns (objs, results dict of numpy arrays).
 

@@ -54,6 +54,12 @@ def _check(case, res, exact_state):
     ("spikegen_period", True),
     ("gapjunction", True),
     ("timedarray", True),
+    # several clocks (stepwise execution, network.cpp:134-159) + `run_regularly` writing shared
+    # variables; a shared variable written on the main clock (persistent kernel: elected writer,
+    # readers behind grid barriers); clock-driven synaptic equations feeding a summed variable
+    ("multiclock", True),
+    ("sharedvar", True),
+    ("synstate", True),
 ])
 def test_spike_exact_persistent(brian, project_dir, case, exact_state):
     model, kwds = CASES[case]
@@ -112,6 +118,27 @@ def test_in_loop_random_numbers_statistics(brian, project_dir):
     assert res["in_spikes_count"].std() > 0
     assert not np.array_equal(res["in_spikes_count"], gold["in_spikes_count"])
     np.testing.assert_allclose(res["G_v"].mean(), gold["G_v"].mean(), rtol=0.1)
+
+
+def test_poisson_function_statistics(brian, project_dir):
+    """`poisson(lam)` in in-loop code (device samplers of csrc/b200_runtime.cuh; reference
+    cpp_generator.py:661-751): means and variances of 4000 x 200 draws for lam = 2.5 (multiplication
+    method) and lam = 40 (PTRS), next to the reference's own run."""
+    model, kwds = CASES["poissonfn"]
+    objs, res = models.run_model(brian, model, "b200", project_dir, **kwds)
+    gold = np.load(os.path.join(GOLDEN, "poissonfn.npz"))
+    steps = 200
+    for key, lam in (("G_acc_small", 2.5), ("G_acc_large", 40.0)):
+        sums = res[key]
+        assert np.all(sums == np.round(sums)) and sums.min() >= 0
+        # sum of `steps` Poisson(lam) draws per neuron: mean and variance steps*lam
+        n = len(sums)
+        assert abs(sums.mean() - steps * lam) < 5 * np.sqrt(steps * lam / n), (key, sums.mean())
+        assert abs(sums.var() - steps * lam) < 6 * steps * lam * np.sqrt(2.0 / n), (key, sums.var())
+        assert abs(sums.mean() - gold[key].mean()) < 7 * np.sqrt(2 * steps * lam / n)
+    for key, lam in (("G_small", 2.5), ("G_large", 40.0)):      # last draw: a single Poisson sample each
+        x = res[key]
+        assert abs(x.mean() - lam) < 5 * np.sqrt(lam / len(x)) and abs(x.var() - lam) < 0.15 * lam
 
 
 def test_float32_mode(brian, project_dir):
