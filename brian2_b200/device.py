@@ -1390,7 +1390,8 @@ class B200Device(CPPStandaloneDevice):
             post_l = np.asarray(local(S.variables["_synaptic_post"]))
             order = mg.sharded_synapse_order(comm.allgather_object(pre_l), comm.allgather_object(post_l))
             seen = set()
-            for var in list(S._registered_variables):
+            # (a set of Variable objects: iterate in an order every rank agrees on)
+            for var in sorted(S._registered_variables, key=lambda v: self.arrays[v]):
                 if var in seen:
                     continue
                 seen.add(var)

@@ -109,13 +109,14 @@ def test_request_stop_ends_the_persistent_kernel_early(brian, project_dir):
         t0 = time.time()
         while b.device._b200_library is None and time.time() - t0 < 60:
             time.sleep(0.01)
-        time.sleep(0.5)
-        b.device._b200_library.request_stop()
+        lib = b.device._b200_library
+        while lib.get_counter("steps") <= 0 and time.time() - t0 < 120:    # the step loop is running
+            time.sleep(0.01)
+        lib.request_stop()
 
     th = threading.Thread(target=stopper)
     th.start()
     b.device.run(directory=project_dir, with_output=False)
     th.join()
     assert 0.0 < b.device._last_run_completed_fraction < 1.0
-    t_end = float(objs["P"].t_[:]) if hasattr(objs["P"], "t_") else 0.0
     assert b.device.counter("steps") < 1e6
