@@ -127,7 +127,13 @@
         // of 32 lines from a device counter instead of fixed shares, so that CTAs that see a
         // slower memory system (far L2 partition) simply take fewer tickets.  The counter of the
         // NEXT step is zeroed above.
-        const bool _dyn = _pw.nbins <= 32 && _nlines >= 64LL * _nwarps;
+        // (only for long rows: many short rows are served by the gather mode below whatever
+        // their number -- a ticket of padded lines would walk its rows one dependent chain after
+        // the other)
+        int _maxlr = _mybin < _pw.nbins ? _blr : 0;
+        #pragma unroll
+        for (int _o = 16; _o > 0; _o >>= 1) _maxlr = max(_maxlr, __shfl_xor_sync(0xffffffffu, _maxlr, _o));
+        const bool _dyn = _pw.nbins <= 32 && _nlines >= 64LL * _nwarps && _maxlr > 4;
         unsigned int* _tickets = _pw.tickets + (_b200_timestep & 1);
         // Many short rows (more rows than warps, every row <= 4 lines: sharded Brunel, COBAHH at
         // high rates): GATHER mode.  A warp takes an equal share of the ROWS, 32 at a time: lane l
@@ -136,9 +142,6 @@
         // the 32 rows into one dense run of slots, and every lane then delivers one slot per
         // pass (all lanes busy however short the rows are; a slot finds its row with a 5-step
         // search over the scanned lengths by shuffles).
-        int _maxlr = _mybin < _pw.nbins ? _blr : 0;
-        #pragma unroll
-        for (int _o = 16; _o > 0; _o >>= 1) _maxlr = max(_maxlr, __shfl_xor_sync(0xffffffffu, _maxlr, _o));
         if (!_dyn && _nrows > _nwarps && _maxlr <= 4)
         {
             const int _ra = (int)(((long long)_gwarp * _nrows) / _nwarps);
