@@ -728,9 +728,31 @@ class B200Device(CPPStandaloneDevice):
         # partition are short latency chains -- each gets its own share of the CTAs instead of
         # all CTAs walking through them one after the other.
         if prefs.devices.b200.split_phases:
+            # Without an end-of-step barrier a CTA that is late out of the last phase is simply
+            # late into the first phase of the next step.  The short latency chains of the last
+            # phase (monitors, compaction) therefore go to the first 1/16 of the CTAs, and the
+            # deliveries of the first phase to the others: the monitors' round trips disappear
+            # behind the deliveries instead of adding to them.
+            heavy0 = [it for it in items if it["phase"] == 0 and not it["owned"] and it.get("weight", 1) > 1]
+            light_last = [it for it in items if it["phase"] == n_phases - 1 and not it["owned"]
+                          and it.get("weight", 1) == 1]
+            stagger = (not end_barrier and n_phases >= 2 and heavy0 and light_last
+                       and len(heavy0) == sum(1 for it in items if it["phase"] == 0 and not it["owned"])
+                       and len(light_last) == sum(1 for it in items if it["phase"] == n_phases - 1 and not it["owned"]))
             for ph in range(n_phases):
                 free = [it for it in items if it["phase"] == ph and not it["owned"]]
-                if len(free) > 1:
+                if stagger and ph in (0, n_phases - 1):
+                    # shares in units of 1/(16 * total): [0, total) = first 1/16 of the grid
+                    total = sum(it.get("weight", 1) for it in free)
+                    acc = 0
+                    for it in free:
+                        w = it.get("weight", 1)
+                        if ph == 0:
+                            it["share"] = (total + 15 * acc, total + 15 * (acc + w), 16 * total)
+                        else:
+                            it["share"] = (acc, acc + w, 16 * total)
+                        acc += w
+                elif len(free) > 1:
                     total = sum(it.get("weight", 1) for it in free)
                     acc = 0
                     for it in free:

@@ -106,6 +106,7 @@ b200::TargetIndex _b200_sv_{{sv}};
 static long long _monN_ub_{{mon.name}} = 0;
 {% endfor %}
 static bool _b200_first_upload = true;
+static unsigned long long _b200_uploaded_epoch = 0;   // host_epoch of the last upload (0: none yet)
 bool _b200_allow_d1 = true;      // prefs.devices.b200.elide_end_barrier
 // monitor records: number of leading elements identical on host and device (see upload_records)
 {% for a in b200_arrays %}
@@ -147,15 +148,23 @@ void _b200_upload()
     _A_host._stop_request = st.stop_request_dev;
     const _B200Clocks _now = _b200_clocks_now();
     (void)_now;
+    // After a run the written arrays are downloaded, so host mirrors and device arrays agree;
+    // as long as nothing on the host touched an array since (host_epoch, bumped by every
+    // host-side write of the generated main()), the next run needs no upload at all.
+    const bool _b200_in_sync = _b200_uploaded_epoch != 0 && _b200_uploaded_epoch == st.host_epoch;
+    _b200_uploaded_epoch = st.host_epoch;
     {% for a in b200_arrays %}
     {% if a.used %}
     {% if a.kind == 'static' %}
-    b200::upload_array(_A_host.{{a.name}}, brian::{{a.name}}, {{a.size}});
+    if (!_b200_in_sync || !_A_host.{{a.name}})
+        b200::upload_array(_A_host.{{a.name}}, brian::{{a.name}}, {{a.size}});
     {% elif a.kind == 'dynamic1d' and a.monitor %}
     b200::upload_records(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}}, _b200_synced{{a.name}});
     {% elif a.kind == 'dynamic1d' %}
-    b200::upload_vector(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}});
+    if (!_b200_in_sync || !_A_host.{{a.name}} || _A_host._n{{a.name}} != brian::{{a.dyn_name}}.size())
+        b200::upload_vector(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}});
     {% elif a.kind == 'dynamic2d' %}
+    if (!_b200_in_sync || !_A_host.{{a.name}} || _A_host._n{{a.name}} != brian::{{a.dyn_name}}.n)
     {
         // row-major (rows x {{a.width}}) append buffer
         const size_t _rows = brian::{{a.dyn_name}}.n, _w = {{a.width}};
@@ -446,6 +455,7 @@ int _b200_array_copy_in(const char* name, const void* data, size_t nbytes)
     _B200HostArray* a = _b200_find_array(name);
     if (!a) return 1;
     try { a->copy_in(data, nbytes); } catch (...) { return 2; }
+    b200::state().host_epoch++;       // the host mirror changed: upload it before the next run
     return 0;
 }
 
