@@ -624,7 +624,7 @@ class CUDACodeGenerator(CPPCodeGenerator):
         kwds["b200_counted"] = access.get("counted")
         kwds["b200_serial"] = serial
         kwds["b200_unroll"] = 1 if serial else getattr(self, "_b200_unroll", 1)
-        kwds["b200_gather_unroll"] = 2 if kwds["b200_unroll"] > 1 else 1
+        kwds["b200_gather_unroll"] = 4 if kwds["b200_unroll"] > 1 else 1
         kwds["b200_preloads"] = [] if serial else list(getattr(self, "_b200_preloads", []))
         # remembered by the device for the barrier analysis of the persistent kernel
         access["serial"] = serial

@@ -103,20 +103,21 @@ def test_request_stop_ends_the_persistent_kernel_early(brian, project_dir):
     objs = models.cuba(b, N=1000, p=0.08, duration=0.0, monitor=False)
     objs["net"].run(100 * b.second, namespace={})              # 10^6 steps: seconds of GPU time
     b.device.build(directory=project_dir, compile=True, run=False, with_output=False)
-    b.device._b200_library = None
+    dev = b.get_device()            # (the real device object, not the `brian2.device` proxy)
+    dev._b200_library = None
 
     def stopper():
         t0 = time.time()
-        while b.device._b200_library is None and time.time() - t0 < 60:
+        while dev._b200_library is None and time.time() - t0 < 60:
             time.sleep(0.01)
-        lib = b.device._b200_library
+        lib = dev._b200_library
         while lib.get_counter("steps") <= 0 and time.time() - t0 < 120:    # the step loop is running
             time.sleep(0.01)
         lib.request_stop()
 
     th = threading.Thread(target=stopper)
     th.start()
-    b.device.run(directory=project_dir, with_output=False)
+    dev.run(directory=project_dir, with_output=False)
     th.join()
-    assert 0.0 < b.device._last_run_completed_fraction < 1.0
-    assert b.device.counter("steps") < 1e6
+    assert 0.0 < dev._last_run_completed_fraction < 1.0
+    assert 0 < dev.counter("steps") < 1e6
