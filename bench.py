@@ -305,6 +305,7 @@ def run_b200(args, rank, world, workload=None, steps=None, warmup=None, sim_step
     clocks = sampler.stop([(cnt(f"run{r}.t0_unix"), cnt(f"run{r}.t0_unix") + cnt(f"run{r}.wall_seconds"))
                            for r in timed])
     dev_s = sum(cnt(f"run{r}.device_seconds") for r in timed)
+    per_run_ms = [round(1e3 * cnt(f"run{r}.device_seconds"), 3) for r in range(n_runs)]
     # end to end = what a user's run() call costs: (re)build of the pathway CSRs if the host
     # arrays changed + upload + step loop + download
     e2e_s = sum(cnt(f"run{r}.prepare_seconds") + cnt(f"run{r}.upload_seconds") + cnt(f"run{r}.wall_seconds")
@@ -334,7 +335,8 @@ def run_b200(args, rank, world, workload=None, steps=None, warmup=None, sim_step
                 build_seconds=build_seconds, run_wall=run_wall,
                 connect_seconds=cnt("connect_seconds"), prepare_seconds=cnt("prepare_seconds"),
                 sim_steps=sim_steps, bytes_neuron=bytes_neuron, bytes_event=bytes_event, e2e_parts=e2e_parts,
-                objs=objs, workload=workload, steps=steps, warmup=warmup, grid=int(cnt("grid")))
+                objs=objs, workload=workload, steps=steps, warmup=warmup, grid=int(cnt("grid")),
+                per_run_ms=per_run_ms)
 
 
 def _project_dir(name, rank):
@@ -548,6 +550,7 @@ def _b200_line(args, r, world, hbm_peak, peak_src):
     line = {
         "metric": "synaptic_events_per_s", "value": events / dev_s, "unit": "events/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / steps,
+        "ms_per_run_rank0": r["per_run_ms"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": _config(r["workload"], r["n_neurons"], n_syn, r["sharded"]),
         "timesteps_per_step": r["sim_steps"],

@@ -66,7 +66,7 @@ extern int _b200_dyn_smem;                   // dynamic shared memory of every k
 void _b200_tiles_reserve();                  // dense counted pathways: shared-memory budget ...
 void _b200_tiles_build();                    // ... and tile tables (csrc/b200_tiles.cuh)
 _B200Clocks _b200_clocks_now();
-void _b200_prepare_steps(long long steps, bool exact);   // make monitor buffers large enough
+void _b200_prepare_steps(long long steps, bool exact, bool count = true);   // make monitor buffers large enough
 void _b200_prefault_start(long long steps);   // host-side: map the pages the next records will land in
 void _b200_prefault_join();
 void _b200_launch_begin(const char* name);
@@ -244,7 +244,7 @@ void _b200_upload()
 // Guarantee that every monitor can record `steps` more steps (exact == true: the true entry
 // counts are read back first; false: cheap host-side upper bounds are used).
 static long long _b200_steps_prepared = 0;   // steps of the earlier launches (event-rate estimate)
-void _b200_prepare_steps(long long steps, bool exact)
+void _b200_prepare_steps(long long steps, bool exact, bool count)
 {
     bool changed = false;
     {% for mon in b200_monitors %}
@@ -305,7 +305,7 @@ void _b200_prepare_steps(long long steps, bool exact)
         {% endif %}
     }
     {% endfor %}
-    if (exact) _b200_steps_prepared += steps;
+    if (exact && count) _b200_steps_prepared += steps;
     if (changed) _b200_sync_constants();
 }
 
@@ -334,6 +334,7 @@ void _b200_prefault_join()
 void _b200_prefault_start(long long steps)
 {
     _b200_prefault_join();
+    if (getenv("B200_NO_PREFAULT")) return;
     {% for mon in b200_monitors %}
     {% if mon.kind == 'spike' %}
     const size_t _need_{{mon.name}} = (size_t)(_monN_ub_{{mon.name}} + (_b200_steps_prepared > steps

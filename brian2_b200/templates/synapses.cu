@@ -440,10 +440,16 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
                     #pragma unroll
                     for (int _r = 0; _r < 4; ++_r)
                     {
-                        #pragma unroll
-                        for (int _u = 0; _u < 3; ++_u)
-                        {
-                            if (_cur[_r][_u] >= 0) _cnt[_cur[_r][_u] - (int)_mine.lo] += 1;
+                        {   // the (up to 96) entries of one row point at distinct targets: their
+                            // three counter updates are independent (loads first, then stores);
+                            // the next row may hit the same counters and has to wait
+                            int _old[3];
+                            #pragma unroll
+                            for (int _u = 0; _u < 3; ++_u)
+                                _old[_u] = _cur[_r][_u] >= 0 ? _cnt[_cur[_r][_u] - (int)_mine.lo] : 0;
+                            #pragma unroll
+                            for (int _u = 0; _u < 3; ++_u)
+                                if (_cur[_r][_u] >= 0) _cnt[_cur[_r][_u] - (int)_mine.lo] = _old[_u] + 1;
                             __syncwarp();
                         }
                         // rows with more than 96 entries in this tile: the rest, line by line
