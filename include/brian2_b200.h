@@ -27,6 +27,12 @@
  *                                   counters bench.py reports: kernel launches, synaptic events,
  *                                   host<->device bytes).
  *
+ * Differences from the sketch in SURVEY.md section 8(b): there is no `b200_init(n_gpus,
+ * static_dir)` -- the runtime initialises itself on the first device call of b200_run_main (the
+ * static arrays are found relative to the working directory exactly like ./main finds them) and
+ * the multi-GPU setup is b200_set_comm; b200_get_array takes the capacity of the caller's buffer
+ * by value and fails if it is too small (the size is asked with b200_get_array_size first).
+ *
  * Conventions: functions returning int return 0 on success, non-zero on failure with the
  * message available from b200_last_error().  The library never calls exit().  Buffers passed in
  * or out are owned by the caller (copy semantics).  Not re-entrant: one run at a time.
@@ -73,13 +79,20 @@ int b200_comm_world(void);
  *   "profile"     1 = per-code-object CUDA-event timing (forces mode 1 semantics per launch)
  *   "ctas_per_sm" resident CTAs per SM used to size grids
  *   "grid"        upper bound on the number of CTAs (0 = none)
- *   "seed"        seed of the device RNG streams */
+ *   "seed"        seed of the device RNG streams (default: drawn from std::random_device unless the
+ *                 script called seed(); rank 0's draw on several GPUs)
+ *   "allow_d1"    1 = use the step kernel without end-of-step barrier when every pathway delivers
+ *                 at least one step after the spike (default), 0 = never
+ *   "tiles"       1 = count dense rows of countable pathways in shared memory over target tiles
+ *                 (default), 0 = always scatter */
 int b200_set_option(const char* key, double value);
 
 /* Counters: "launches", "events" (delivered synaptic events), "steps", "h2d_bytes",
- * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "grid", "runs", and per
+ * "d2h_bytes", "upload_seconds", "download_seconds", "device_bytes", "num_sms", "grid", "runs",
+ * "connect_seconds|connect_synapses|connect_launches" (synapse creation on the device),
+ * "prepare_seconds" (host time building pathway CSRs), "all_delayed", "dyn_smem", and per
  * Network::run call "run<i>.device_seconds|wall_seconds|t0_unix|upload_seconds|download_seconds|
- * events|steps|persistent"; "phase<k*512+i>" = cycles sampled CTA k (first, 1/4, 3/4, last of the
+ * prepare_seconds|events|steps|persistent"; "phase<k*512+i>" = cycles sampled CTA k (first, 1/4, 3/4, last of the
  * grid) spent in phase i of the persistent kernel (profile_phases builds).  -1 if unknown. */
 double b200_get_counter(const char* key);
 
