@@ -19,10 +19,11 @@ def _select_host_compiler():
     code once the library is dlopen()ed into Python -- and cannot link -fopenmp."""
     if os.environ.get("B200_KEEP_CXX"):
         return
-    if os.path.exists("/usr/bin/g++"):
-        os.environ["CXX"] = "/usr/bin/g++"
-    if os.path.exists("/usr/bin/gcc"):
-        os.environ["CC"] = "/usr/bin/gcc"
+    # only replace what is unset or known to be unusable; any other choice of the user stands
+    for var, good in (("CXX", "/usr/bin/g++"), ("CC", "/usr/bin/gcc")):
+        current = os.environ.get(var, "")
+        if os.path.exists(good) and (not current or current.startswith("/opt/gcc/")):
+            os.environ[var] = good
 
 
 def ensure_brian2_importable():

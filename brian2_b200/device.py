@@ -1311,7 +1311,6 @@ class B200Device(CPPStandaloneDevice):
                 if acc.get("serial"):
                     raise NotImplementedError("b200 multi-GPU: order-dependent synaptic code")
                 pathway = info["template_kwds"]["pathway"]
-                pre_idx = "_presynaptic_idx" if pathway.prepost == "pre" else "_postsynaptic_idx"
                 for name in codeobj.variables:
                     if codeobj.variable_indices[name] == "_presynaptic_idx":
                         var = codeobj.variables[name]

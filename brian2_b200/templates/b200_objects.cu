@@ -148,6 +148,21 @@ void _b200_upload()
     _A_host._stop_request = st.stop_request_dev;
     const _B200Clocks _now = _b200_clocks_now();
     (void)_now;
+    // Event monitors record into device append buffers.  Growing one (allocate, copy, free) costs
+    // hundreds of milliseconds once the buffers are large, so they start with a share of the
+    // device memory that is free at this point: 1/8 of it, split over all record buffers.
+    static size_t _b200_record_entries = 0;
+    if (_b200_record_entries == 0) {
+        size_t _free = 0, _total = 0, _bytes = 0;
+        {% for a in b200_arrays %}
+        {% if a.used and a.kind == 'dynamic1d' and a.monitor %}
+        _bytes += sizeof({{a.ctype}});
+        {% endif %}
+        {% endfor %}
+        if (_bytes && cudaMemGetInfo(&_free, &_total) == cudaSuccess)
+            _b200_record_entries = std::min<size_t>(_free / 8 / _bytes, (size_t)1 << 30);
+        _b200_record_entries = std::max<size_t>(_b200_record_entries, 1);
+    }
     // After a run the written arrays are downloaded, so host mirrors and device arrays agree;
     // as long as nothing on the host touched an array since (host_epoch, bumped by every
     // host-side write of the generated main()), the next run needs no upload at all.
@@ -159,7 +174,7 @@ void _b200_upload()
     if (!_b200_in_sync || !_A_host.{{a.name}})
         b200::upload_array(_A_host.{{a.name}}, brian::{{a.name}}, {{a.size}});
     {% elif a.kind == 'dynamic1d' and a.monitor %}
-    b200::upload_records(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}}, _b200_synced{{a.name}});
+    b200::upload_records(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, std::max<size_t>((size_t){{a.min_cap}}, _b200_record_entries), _b200_synced{{a.name}});
     {% elif a.kind == 'dynamic1d' %}
     if (!_b200_in_sync || !_A_host.{{a.name}} || _A_host._n{{a.name}} != brian::{{a.dyn_name}}.size())
         b200::upload_vector(_A_host.{{a.name}}, _A_host._cap{{a.name}}, _A_host._n{{a.name}}, brian::{{a.dyn_name}}, (size_t){{a.min_cap}});
