@@ -51,7 +51,7 @@ constexpr size_t kTileSmem = (size_t)kWarps * kMaxTile * sizeof(int);
 // Could this pathway be served by tiles on a grid of about `grid_guess` CTAs?  (Decides the
 // dynamic shared memory of the step kernels before the grid size is final.)
 inline bool tiles_candidate(const Pathway& pw, int grid_guess) {
-    if (!pw.prepared || pw.tile_n <= 0 || pw.nbins <= 0 || pw.n_owned == 0) return false;
+    if (!pw.prepared || pw.forward || pw.tile_n <= 0 || pw.nbins <= 0 || pw.n_owned == 0) return false;
     const double nrows = (double)pw.nbins * (double)std::max(1, pw.spikes_stop - pw.spikes_start);
     return (double)pw.n_owned / nrows >= 8.0 * (double)grid_guess;
 }

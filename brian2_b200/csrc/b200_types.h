@@ -70,6 +70,9 @@ struct PathwayDev {
                               // thresholder's segments, -1: none (older lists: compacted form)
     int* hits;                // counted pathways: [2][hits_n] events per target, by step parity
     int hits_n;
+    int hits_slots;           // 2 (by step parity), or max_delay + 1 in the forward layout
+    int forward;              // 1: CSR by (source, delay bin), bin in the top 5 bits of csr_target,
+                              // rowptr[nsrc][nbins + 1]; a spike is delivered once, one step later
     const int* tileptr;       // dense rows (b200_tiles.cuh): [nbins][nsrc + 1][grid + 1] first slot of
                               // the row at or after the first target of every CTA's block; 0: none
     int tile_stride;          // ints between the per-warp counter arrays in shared memory

@@ -139,6 +139,16 @@ prefs.register_preferences(
     grid=BrianPreference(
         default=0, docs="Upper bound on the number of CTAs of every kernel (0: no bound)."
     ),
+    forward_delivery=BrianPreference(
+        default=True,
+        docs="""
+        Counted pathways whose delays are all at least one time step (and at most 32 distinct
+        values): store the synapses by (source, delay) and deliver every spike ONCE, one step
+        after it was emitted, into per-target counters of the step in which each synapse is due
+        (a ring of ``max_delay + 1`` counter arrays), instead of once per delay value from a spike
+        list of the right age.
+        """,
+    ),
     tiled_delivery=BrianPreference(
         default=True,
         docs="""
@@ -1263,6 +1273,7 @@ class B200Device(CPPStandaloneDevice):
         lib.set_option("grid", int(prefs.devices.b200.grid))
         lib.set_option("allow_d1", 1 if prefs.devices.b200.elide_end_barrier else 0)
         lib.set_option("tiles", 1 if prefs.devices.b200.tiled_delivery else 0)
+        lib.set_option("forward", 1 if prefs.devices.b200.forward_delivery else 0)
         comm = self.communicator()
         if comm.world > 1:
             self._check_multi_gpu_support()

@@ -94,7 +94,7 @@ b200::EventSpace _b200_es{{es.name}};
 {% endfor %}
 namespace brian {
 {% for pw in b200_pathways %}
-b200::Pathway {{pw.name}}({{pw.sources}}, {{pw.start}}, {{pw.stop}});
+b200::Pathway {{pw.name}}({{pw.sources}}, {{pw.start}}, {{pw.stop}}, {{pw.hits_n}});
 {% endfor %}
 }
 {% for sv in b200_summed %}

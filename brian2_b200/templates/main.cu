@@ -145,6 +145,7 @@ int b200_set_option(const char* key, double value)
     else if (k == "grid") _b200_grid_override = (int)value;
     else if (k == "allow_d1") _b200_allow_d1 = value != 0;
     else if (k == "tiles") _b200_allow_tiles = value != 0;
+    else if (k == "forward") b200::Pathway::allow_forward() = value != 0;
     else if (k == "seed") { b200::state().seed = (unsigned long long)value; b200::state().seeded = true; }
     else return 1;
     return 0;

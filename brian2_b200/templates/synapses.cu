@@ -49,7 +49,53 @@
     {% if not b200_counted.dual %}
     // counted pathway: the delivery only counts the events per target (integer reductions);
     // the owner of every target applies them afterwards (_dev_{{codeobj_name}}_apply below)
-    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep % _pw.hits_slots) * (size_t)_pw.hits_n;
+    if (_pw.forward)
+    {
+        // ---- FORWARD delivery (every delay >= 1 step; CSR by (source, delay bin), see
+        // Pathway::prepare): the spikes of the PREVIOUS step are delivered now, each row once and
+        // contiguous, into the counters of the steps in which the synapses are due.
+        const int _lane = threadIdx.x & 31;
+        const int _gwarp = _ctx.bid * b200::kWarps + (threadIdx.x >> 5);
+        const int _nwarps = _ctx.nb * b200::kWarps;
+        const int _R = _pw.hits_slots, _nb = _pw.nbins;
+        const int _bdelay = _lane < _nb ? __ldg(_pw.bin_delay + _lane) : 0;
+        const b200::SpikeView _view = b200::view_build(_es, _b200_timestep - 1, _ctx, false, _A._ctrl);
+        const int _nrows = _view.total;
+        const int _base_slot = (int)((_b200_timestep - 1) % _R);      // slot of delay 0 (never used: delays >= 1)
+        unsigned long long _nev = 0ULL;
+        // fewer rows than warps: _k warps share a row; else a warp takes whole rows
+        const int _k = _nrows > 0 && _nrows < _nwarps ? _nwarps / _nrows : 1;
+        for (int _r = _gwarp / _k; _r < _nrows; _r += max(1, _nwarps / _k))
+        {
+            const int _part = _gwarp - (_gwarp / _k) * _k;
+            const int _src = b200::view_id(_view, _r) - _pw.src_start;
+            if (_src < 0 || _src >= _pw.nsrc) continue;
+            const int* _rp = _pw.rowptr + (size_t)_src * (size_t)(_nb + 1);
+            const int _beg = __ldg(_rp), _end = __ldg(_rp + _nb);
+            if (_part == 0) _nev += (unsigned long long)(_end - _beg);
+            const int _per = (((_end - _beg + _k - 1) / _k) + 31) & ~31;
+            const int _a = _beg + _part * _per, _b = min(_end, _a + _per);
+            for (int _kb = _a + _lane; _kb - _lane < _b; _kb += 32 * 4)
+            {
+                unsigned int _w[4];
+                #pragma unroll
+                for (int _u = 0; _u < 4; ++_u)
+                    _w[_u] = _kb + 32 * _u < _b ? (unsigned int)b200::ld_index(_pw.csr_target + _kb + 32 * _u) : 0xffffffffu;
+                #pragma unroll
+                for (int _u = 0; _u < 4; ++_u)
+                {
+                    const unsigned int _bin = _w[_u] == 0xffffffffu ? 0u : (_w[_u] >> 27);
+                    int _slot = _base_slot + __shfl_sync(0xffffffffu, _bdelay, (int)_bin);
+                    if (_slot >= _R) _slot -= _R;
+                    if (_w[_u] != 0xffffffffu)
+                        atomicAdd(_pw.hits + (size_t)_slot * (size_t)_pw.hits_n + (_w[_u] & 0x7ffffffu), 1);
+                }
+            }
+        }
+        if (_lane == 0 && _nev) atomicAdd(_pw.events, _nev);
+        return;
+    }
     {% endif %}
     if (_pw.tileptr) return;    // dense rows: counted AND applied by the owners of the targets (apply pass)
     {% endif %}
@@ -496,13 +542,13 @@ __device__ __forceinline__ void _dev_{{codeobj_name}}_apply(const b200::Ctx& _ct
     {% if b200_counted.dual %}
     // (sparse rows of this pathway are delivered by floating-point reductions: nothing to apply)
     {% else %}
-    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep & 1) * (size_t)_pw.hits_n;
+    int* _b200_hits = _pw.hits + (size_t)(_b200_timestep % _pw.hits_slots) * (size_t)_pw.hits_n;
     B200_FOR_OWNED(_i64, (int64_t){{b200_counted.size}}, _ctx)
     {
         const int _b200_tgt_idx = (int)_i64;
         const int _b200_n = __ldcg(_b200_hits + _b200_tgt_idx);
         if (_b200_n == 0) continue;
-        _b200_hits[_b200_tgt_idx] = 0;      // this buffer is counted into again two steps from now
+        _b200_hits[_b200_tgt_idx] = 0;      // this slot is counted into again a whole ring later
         const int _idx = _b200_tgt_idx;
         const int _vectorisation_idx = _idx;
         {{b200_apply_loads|autoindent}}

@@ -83,6 +83,7 @@ int b200_comm_world(void);
  *                 script called seed(); rank 0's draw on several GPUs)
  *   "allow_d1"    1 = use the step kernel without end-of-step barrier when every pathway delivers
  *                 at least one step after the spike (default), 0 = never
+ *   "forward"     1 = forward delivery of counted pathways with delays >= 1 step (default), 0 = off
  *   "tiles"       1 = count dense rows of countable pathways in shared memory over target tiles
  *                 (default), 0 = always scatter */
 int b200_set_option(const char* key, double value);

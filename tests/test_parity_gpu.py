@@ -214,10 +214,24 @@ def test_monitors_of_subgroups(brian, project_dir):
     _check("submon", res, True)
 
 
-def test_two_run_calls_equal_one(brian, project_dir):
+@pytest.mark.parametrize("case", ["cuba_1000", "brunel_hetero"])
+def test_two_run_calls_equal_one(brian, project_dir, case):
     """`run(50 ms); run(50 ms)` leaves exactly the records and state of the reference's single
-    `run(100 ms)`: the device state, the spike ring and the monitor records (transferred
-    incrementally, b200_host.h: upload_records / download_records) carry over between runs."""
-    model, kwds = CASES["cuba_1000"]
+    `run(100 ms)`: the device state, the spike ring, the events that are still in flight (forward
+    delivery: counters of future steps) and the monitor records (transferred incrementally,
+    b200_host.h: upload_records / download_records) carry over between runs."""
+    model, kwds = CASES[case]
     objs, res = models.run_model(brian, model, "b200", project_dir, n_runs=2, **kwds)
-    _check("cuba_1000", res, True)
+    _check(case, res, True)
+
+
+def test_forward_delivery_can_be_switched_off(brian, project_dir):
+    """Brunel with 20 delay values by the per-delay-bin delivery (compacted lists of the right
+    age) instead of the forward layout: same bits."""
+    model, kwds = CASES["brunel_hetero"]
+    try:
+        objs, res = models.run_model(brian, model, "b200", project_dir,
+                                     prefs_update={"devices.b200.forward_delivery": False}, **kwds)
+    finally:
+        brian.prefs["devices.b200.forward_delivery"] = True
+    _check("brunel_hetero", res, True)
