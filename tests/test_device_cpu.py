@@ -108,7 +108,8 @@ def test_counted_pathway_code_of_brunel(brian):
     and the owner applies `if(not_refractory) v += J` once per counted event."""
     import __graft_entry__ as ge
 
-    directory, _ = ge.build_project("brunel_hetero", directory=os.path.join(ge.PREBUILT, "cpu_brunel_hetero"))
+    directory, _ = ge.build_project("brunel_hetero", directory=os.path.join(ge.PREBUILT, "cpu_brunel_hetero"),
+                                    compile=False)
     code = open(os.path.join(directory, "code_objects", "brunel_exc_pre_codeobject.cuh")).read()
     deliver = code.split("__device__ __forceinline__ void _dev_brunel_exc_pre_codeobject(")[1].split("__global__")[0]
     assert "atomicAdd(_b200_hits + _b200_tgt_idx, 1);" in deliver
@@ -304,7 +305,7 @@ def test_generated_propagation_code_of_ragged_case(ragged_project):
 def _plans_of(case):
     import __graft_entry__ as ge
 
-    directory, _ = ge.build_project(case, directory=os.path.join(ge.PREBUILT, "cpu_" + case))
+    directory, _ = ge.build_project(case, directory=os.path.join(ge.PREBUILT, "cpu_" + case), compile=False)
     return _schedules(open(os.path.join(directory, "b200_kernels.cu")).read())
 
 
