@@ -1,12 +1,13 @@
-"""Recipe that installs the UNMODIFIED reference (brian-team/brian2) into ``oracle/_ref/``.
+"""Recipe that installs the UNMODIFIED reference (brian-team/brian2) into ``baseline/_ref/``.
 
-TEST INFRASTRUCTURE ONLY.  ``oracle/_ref`` is git-ignored (never part of history) but is *not*
+``baseline/_ref`` is git-ignored (never part of history) but is *not*
 gpurun-ignored, so it travels to the GPU box exactly like our own built ``.so`` files.  It is
 used for three things and nothing else:
 
 * as the front-end the ``b200`` device plugs into (equations, ``Synapses.connect`` ... are the
   reference's own, untouched -- BASELINE.json north_star),
-* as the parity oracle (``set_device('cpp_standalone')``, serial, strict flags), and
+* as the parity oracle that generates the golden vectors (``set_device('cpp_standalone')``, serial,
+  strict flags; tests/golden/make_golden.py), and
 * as the CPU baseline arm of ``bench.py`` (``cpp_standalone`` + OpenMP on the box's host cores).
 
 Recipe (verified): copy the package where it lies under /root/reference,

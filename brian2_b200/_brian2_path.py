@@ -2,15 +2,15 @@
 
 The device is a *plugin*: equations, ``NeuronGroup``/``Synapses``/monitors, ``Synapses.connect``
 and the state updaters are Brian2's own (BASELINE.json north_star).  If ``brian2`` is not
-already importable, fall back to the scripted install under ``oracle/_ref`` (see
-``oracle/install_ref.py``; git-ignored, travels to the GPU box with the snapshot).
+already importable, fall back to the scripted install of the unmodified reference under
+``baseline/_ref`` (see ``baseline/install_ref.py``; git-ignored, travels to the GPU box with the snapshot).
 """
 import importlib.util
 import os
 import sys
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_DIR = os.path.join(REPO_ROOT, "oracle", "_ref")
+REF_DIR = os.path.join(REPO_ROOT, "baseline", "_ref")
 
 
 def _select_host_compiler():
@@ -36,6 +36,6 @@ def ensure_brian2_importable():
         sys.path.insert(0, REF_DIR)
         return
     raise ImportError(
-        "brian2 is not importable and oracle/_ref is not populated; run "
-        "`python oracle/install_ref.py` (needs /root/reference) or install brian2"
+        "brian2 is not importable and baseline/_ref is not populated; run "
+        "`python baseline/install_ref.py` (needs /root/reference) or install brian2"
     )

@@ -40,7 +40,7 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def brian():
-    """The Brian2 front-end (reference install under oracle/_ref) with the b200 device registered."""
+    """The Brian2 front-end (reference install under baseline/_ref) with the b200 device registered."""
     import brian2_b200  # noqa: F401  (registers the device, makes brian2 importable)
     import brian2
 

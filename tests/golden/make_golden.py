@@ -2,7 +2,7 @@
 (brian-team/brian2, `cpp_standalone` device, serial, strict floating-point flags -- SURVEY.md
 section 8c) on the model scripts of tests/models.py.
 
-Run in the build container (needs oracle/_ref, i.e. /root/reference):
+Run in the build container (needs baseline/_ref, i.e. /root/reference):
     python tests/golden/make_golden.py [case ...]
 The resulting .npz files are committed; the GPU box never needs the reference to check parity.
 """

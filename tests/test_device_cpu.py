@@ -145,7 +145,7 @@ def test_no_cpu_fallback_without_gpu(cuba_project):
 
 def test_product_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under brian2_b200/ may import, link or run it
-    (the reference *front-end* under oracle/_ref is located by _brian2_path.py only)."""
+    (the reference *front-end* lives under baseline/_ref, located by _brian2_path.py)."""
     pkg = os.path.join(ROOT, "brian2_b200")
     offenders = []
     for dirpath, dirnames, filenames in os.walk(pkg):

@@ -44,7 +44,7 @@ def test_spikequeue_against_reference_cython_queue():
     """Random pushes: the restatement and the reference's compiled CSpikeQueue (through its
     Cython wrapper, synapses/cythonspikequeue.pyx) must deliver identical buckets, in order."""
     try:
-        import brian2_b200  # noqa: F401  (puts oracle/_ref on sys.path)
+        import brian2_b200  # noqa: F401  (puts baseline/_ref on sys.path)
         from brian2.synapses.cythonspikequeue import SpikeQueue as RefQueue
     except ImportError:
         pytest.skip("reference spike queue extension not built")
