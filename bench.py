@@ -61,6 +61,18 @@ WORKLOADS = {
     "synapses_only_highrate": ("synapses_only", dict(N=100000, p=0.2, rate_hz=100.0), 0.0, 20.0),
 }
 
+#: what actually bounds a step of each model family (ncu, profiles/): `roofline.bound` names the
+#: roofline the contract asks for, this says why the fraction is what it is
+LIMITERS = {
+    "cobahh": "instruction issue (fp64 exp/expm1 chains, ~900 warp instructions per 32 neurons) + 2 grid barriers; "
+              "working set L2 resident (DRAM 0.4 MB/step)",
+    "cuba": "latency: ~14 dependent L2 round trips per step (grid size 4...296 CTAs changes nothing)",
+    "brunel": "latency: delivery = chain of 4-5 dependent loads, one grid barrier per step",
+    "synapses": "shared-memory pipe of the tiled delivery (LDS+STS per 32 events); index stream L2 resident",
+    "potjans": "latency: delivery chain over 45 delay bins + 2 grid barriers",
+    "stdp": "latency: on_pre -> barrier -> on_post over 100k synapses of one neuron",
+}
+
 #: device preferences of a workload (everything else runs with the defaults)
 WORKLOAD_PREFS = {
     "brunel_125k_sharded": {"devices.b200.construction": "sharded"},
@@ -579,6 +591,7 @@ def _b200_line(args, r, world, hbm_peak, peak_src):
                      "algorithmic_bytes_per_launch": algo_bytes / max(steps, 1),
                      "peak_source": peak_src,
                      "kernel": "persistent step kernel (stateupdate+threshold+propagation+monitors)",
+                     "limiter": LIMITERS.get(r["workload"].split("_")[0], "latency: dependent L2 round trips + grid barriers"),
                      "algorithmic_bytes": f"{bytes_neuron} B/neuron-step + {bytes_event} B/event",
                      "propagation_only": {"achieved": prop_bytes / r["dev_s"] / 1e9,
                                           "frac": prop_bytes / r["dev_s"] / 1e9 / hbm_peak,

@@ -1,9 +1,13 @@
 // Bit-identity of the constant-bank exp/expm1 (brian2_b200/csrc/b200_functions.cuh) with CUDA's
 // library functions, the ones the parity tolerances were established with.  Prints
-// "<function> <number of arguments> <number of mismatches>" per function.
+// "<function> <number of arguments> <number of mismatches>" per function, then the distance to
+// the HOST's glibc (the arithmetic of the reference's cpp_standalone, i.e. of the oracle) over
+// 10^7 arguments of the Hodgkin-Huxley range: "<function>_vs_glibc <n> <differing> <max ulp>".
 #include <cstdio>
 #include <cstdint>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "b200_functions.cuh"
 
@@ -38,6 +42,48 @@ __global__ void check(unsigned long long n, int mode, unsigned long long* bad_ex
     if (br) atomicAdd(bad_exprel, br);
 }
 
+// ---- against the ORACLE's arithmetic: the host's glibc (what cpp_standalone links) -----------
+__global__ void eval_hh(unsigned long long n, double* x, double* e, double* m) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        x[i] = make_arg(i, 1);                 // the Hodgkin-Huxley argument range, |x| < 50
+        e[i] = _b200_exp(x[i]);
+        m[i] = _b200_expm1(x[i]);
+    }
+}
+
+static long long ulp_distance(double a, double b) {
+    long long ia, ib;
+    memcpy(&ia, &a, 8);
+    memcpy(&ib, &b, 8);
+    if (ia < 0) ia = (long long)0x8000000000000000ULL - ia;
+    if (ib < 0) ib = (long long)0x8000000000000000ULL - ib;
+    return ia > ib ? ia - ib : ib - ia;
+}
+
+static void against_glibc() {
+    const unsigned long long n = 10000000ULL;          // 10^7 arguments
+    double *dx, *de, *dm;
+    cudaMalloc(&dx, n * 8); cudaMalloc(&de, n * 8); cudaMalloc(&dm, n * 8);
+    eval_hh<<<592, 256>>>(n, dx, de, dm);
+    double* hx = (double*)malloc(n * 8); double* he = (double*)malloc(n * 8); double* hm = (double*)malloc(n * 8);
+    cudaMemcpy(hx, dx, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(he, de, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hm, dm, n * 8, cudaMemcpyDeviceToHost);
+    long long max_e = 0, max_m = 0;
+    unsigned long long diff_e = 0, diff_m = 0;
+    for (unsigned long long i = 0; i < n; ++i) {
+        const long long ue = ulp_distance(he[i], exp(hx[i])), um = ulp_distance(hm[i], expm1(hx[i]));
+        if (ue) diff_e++;
+        if (um) diff_m++;
+        if (ue > max_e) max_e = ue;
+        if (um > max_m) max_m = um;
+    }
+    // "<function>_vs_glibc <arguments> <results that differ> <largest distance in ulp>"
+    printf("exp_vs_glibc %llu %llu %lld\nexpm1_vs_glibc %llu %llu %lld\n", n, diff_e, max_e, n, diff_m, max_m);
+    free(hx); free(he); free(hm); cudaFree(dx); cudaFree(de); cudaFree(dm);
+}
+
 int main() {
     unsigned long long* d;
     if (cudaMalloc(&d, 3 * sizeof(unsigned long long)) != cudaSuccess) { printf("no device\n"); return 2; }
@@ -52,5 +98,6 @@ int main() {
         args += n;
     }
     printf("exp %llu %llu\nexpm1 %llu %llu\nexprel %llu %llu\n", args, tot[0], args, tot[1], args, tot[2]);
+    against_glibc();
     return (tot[0] | tot[1] | tot[2]) ? 1 : 0;
 }
