@@ -430,6 +430,45 @@ public:
         tiles_tried = false;
     }
 
+    // Forward layout (see prepare()): synapses ordered by (source, delay bin, synapse index);
+    // rowptr[s * (nbins + 1) + b] = first slot of bin b of source s, rowptr[s * (nbins + 1) + nbins]
+    // = one past the last slot of source s; csr_target[slot] = bin << 27 | target.  Pure host
+    // code (tests/cuda/forward_csr_test.cpp checks it on the CPU).  `bins` = nullptr: one bin.
+    template <typename Owned>
+    static size_t build_forward_csr(int nsrc, int nbins, int spikes_start, const int* srcs, const int* targets,
+                                    const int* bins, size_t n_syn, Owned owned, std::vector<int>& rowptr,
+                                    std::vector<int>& csr_target) {
+        const size_t stride = (size_t)nbins + 1;
+        rowptr.assign((size_t)nsrc * stride + 1, 0);
+        std::vector<int> count((size_t)nsrc * nbins + 1, 0);
+        size_t kept = 0;
+        for (size_t i = 0; i < n_syn; ++i) {
+            const int sidx = srcs[i] - spikes_start;
+            if (sidx < 0 || sidx >= nsrc) throw std::runtime_error("b200: synapse source outside pathway source range");
+            if (!owned(i)) continue;
+            count[(size_t)sidx * nbins + (bins ? bins[i] : 0)]++;
+            kept++;
+        }
+        int run = 0;
+        for (int sidx = 0; sidx < nsrc; ++sidx) {
+            for (int b = 0; b < nbins; ++b) {
+                rowptr[(size_t)sidx * stride + b] = run;
+                run += count[(size_t)sidx * nbins + b];
+            }
+            rowptr[(size_t)sidx * stride + nbins] = run;
+        }
+        csr_target.assign(kept, 0);
+        std::vector<int> cursor((size_t)nsrc * nbins);
+        for (int sidx = 0; sidx < nsrc; ++sidx)
+            for (int b = 0; b < nbins; ++b) cursor[(size_t)sidx * nbins + b] = rowptr[(size_t)sidx * stride + b];
+        for (size_t i = 0; i < n_syn; ++i) {
+            if (!owned(i)) continue;
+            const int sidx = srcs[i] - spikes_start, b = bins ? bins[i] : 0;
+            csr_target[cursor[(size_t)sidx * nbins + b]++] = (int)(((unsigned int)b << 27) | (unsigned int)targets[i]);
+        }
+        return kept;
+    }
+
     // Build the delay-binned CSR.  Delay rounding as CSpikeQueue::prepare (spikequeue.h:90):
     // steps = (int)(delay/dt + 0.5); n_delays == 1 means one delay for all synapses (:104).
     // Slot order = (delay bin asc, source asc, synapse index asc); walking the bins from the
@@ -513,37 +552,9 @@ public:
                 if (targets[i] < 0 || targets[i] >= (1 << 27)) forward = false;
         }
         if (forward) {
-            const size_t stride = (size_t)nbins + 1;
-            std::vector<int> rowptr((size_t)nsrc * stride + 1, 0);
-            // row (s, b) starts at rowptr[s * stride + b]; rowptr[s * stride + nbins] = end of source s
-            std::vector<int> count((size_t)nsrc * nbins + 1, 0);
-            n_owned = 0;
-            for (size_t i = 0; i < n_syn; ++i) {
-                const int sidx = srcs[i] - spikes_start;
-                if (sidx < 0 || sidx >= nsrc) throw std::runtime_error("b200: synapse source outside pathway source range");
-                if (!owned(i)) continue;
-                count[(size_t)sidx * nbins + (hetero ? dsteps[i] : 0)]++;
-                n_owned++;
-            }
-            int run = 0;
-            for (int sidx = 0; sidx < nsrc; ++sidx) {
-                for (int b = 0; b < nbins; ++b) {
-                    rowptr[(size_t)sidx * stride + b] = run;
-                    run += count[(size_t)sidx * nbins + b];
-                }
-                rowptr[(size_t)sidx * stride + nbins] = run;
-            }
-            std::vector<int> csr_target(n_owned);
-            {
-                std::vector<int> cursor((size_t)nsrc * nbins);
-                for (int sidx = 0; sidx < nsrc; ++sidx)
-                    for (int b = 0; b < nbins; ++b) cursor[(size_t)sidx * nbins + b] = rowptr[(size_t)sidx * stride + b];
-                for (size_t i = 0; i < n_syn; ++i) {
-                    if (!owned(i)) continue;
-                    const int sidx = srcs[i] - spikes_start, b = hetero ? dsteps[i] : 0;
-                    csr_target[cursor[(size_t)sidx * nbins + b]++] = (int)(((unsigned int)b << 27) | (unsigned int)targets[i]);
-                }
-            }
+            std::vector<int> rowptr, csr_target;
+            n_owned = build_forward_csr(nsrc, nbins, spikes_start, srcs, targets, hetero ? dsteps.data() : nullptr,
+                                        n_syn, owned, rowptr, csr_target);
             identity = false;
             std::vector<int> bin_info(bin_delay.begin(), bin_delay.end());
             bin_info.resize(2 * nbins, 0);

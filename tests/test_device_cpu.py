@@ -407,3 +407,17 @@ def test_sharded_connect_kernels_compile(brian):
     assert "b200::SynapseRng _b200_synrng_rand(" in init and "brian::_random_generators" not in init
     # the reference's host connect is not generated for these objects
     assert not os.path.exists(os.path.join(directory, "code_objects", "sc_cond_synapses_create_generator_codeobject.cpp"))
+
+
+def test_forward_csr_layout_on_the_host(tmp_path):
+    """`b200::Pathway::build_forward_csr` (csrc/b200_host.h): the (source, delay bin) layout of the
+    forward delivery, checked on the CPU against a brute-force grouping of random synapses (with
+    and without the partition filter of multi-GPU runs)."""
+    exe = str(tmp_path / "forward_csr_test")
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "brian2_b200", "csrc"),
+                           "-I", os.path.join(cuda_home, "include"),
+                           os.path.join(ROOT, "tests", "cuda", "forward_csr_test.cpp"), "-o", exe,
+                           "-L", os.path.join(cuda_home, "lib64"), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout + out.stderr
