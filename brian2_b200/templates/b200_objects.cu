@@ -110,7 +110,7 @@ static unsigned long long _b200_uploaded_epoch = 0;   // host_epoch of the last 
 bool _b200_allow_d1 = true;      // prefs.devices.b200.elide_end_barrier
 // monitor records: number of leading elements identical on host and device (see upload_records)
 {% for a in b200_arrays %}
-{% if a.used and a.kind == 'dynamic1d' and a.monitor %}
+{% if a.used and ((a.kind == 'dynamic1d' and a.monitor) or a.kind == 'dynamic2d') %}
 static size_t _b200_synced{{a.name}} = 0;
 {% endif %}
 {% endfor %}
@@ -400,12 +400,16 @@ void _b200_download()
     {% endif %}
     {% elif a.kind == 'dynamic2d' %}
     {
+        // rows recorded by earlier runs are already on the host (append-only records)
         const size_t _rows = (size_t)_monN_{{a.monitor}}, _w = {{a.width}};
-        std::vector<{{a.ctype}}> _tmp(_rows * _w);
-        if (_rows) B200_CUDA(cudaMemcpy(_tmp.data(), _A_host.{{a.name}}, _tmp.size()*sizeof({{a.ctype}}), cudaMemcpyDeviceToHost));
+        size_t _from = (brian::{{a.dyn_name}}.n == _b200_synced{{a.name}} && brian::{{a.dyn_name}}.m == _w
+                        && _rows >= _b200_synced{{a.name}}) ? _b200_synced{{a.name}} : 0;
+        std::vector<{{a.ctype}}> _tmp((_rows - _from) * _w);
+        if (_rows > _from) B200_CUDA(cudaMemcpy(_tmp.data(), _A_host.{{a.name}} + _from * _w, _tmp.size()*sizeof({{a.ctype}}), cudaMemcpyDeviceToHost));
         brian::{{a.dyn_name}}.resize(_rows, _w);
-        for (size_t i = 0; i < _rows; i++) for (size_t j = 0; j < _w; j++) brian::{{a.dyn_name}}(i, j) = _tmp[i*_w + j];
+        for (size_t i = _from; i < _rows; i++) for (size_t j = 0; j < _w; j++) brian::{{a.dyn_name}}(i, j) = _tmp[(i - _from)*_w + j];
         b200::state().d2h_bytes += _tmp.size()*sizeof({{a.ctype}});
+        _b200_synced{{a.name}} = _rows;
     }
     {% endif %}
     {% endif %}
