@@ -54,6 +54,9 @@ WORKLOADS = {
     # per-synapse weights and delays, DC background (deterministic); 50 B/neuron-step, 28 B/event
     "potjans_77k": ("potjans", dict(scale=1.0), 50.0, 28.0),
     "potjans_8k": ("potjans", dict(scale=0.1), 50.0, 28.0),
+    # the same microcircuit with its Poisson background (8 PoissonInput objects, binomial sampler on
+    # the device's Philox streams) instead of the mean current
+    "potjans_77k_poisson": ("potjans", dict(scale=1.0, poisson=True), 50.0, 28.0),
     # propagation stress (brian2/tests/features/speed.py:263-326 SynapsesOnly): every source spikes
     # every step, `w += 1.0` per event -> the step is synaptic propagation only (20 B/event)
     "synapses_only_sparse": ("synapses_only", dict(N=100000, p=0.2, rate_hz=10.0), 0.0, 20.0),
@@ -86,7 +89,7 @@ EXTRA_CONFIGS = ["brunel_125k_sharded"]
 # simulation timesteps (dt = 0.1 ms) of one bench step = one run() call
 DEFAULT_SIM_STEPS = {"cobahh_256k": 4000, "cuba_256k": 4000, "cuba_4k": 10000, "cobahh_4k": 10000,
                      "brunel_100k": 2000, "brunel_125k": 1000, "brunel_125k_sharded": 1000,
-                     "brunel_125k_poisson": 1000, "stdp_100k": 5000, "potjans_77k": 1000,
+                     "brunel_125k_poisson": 1000, "stdp_100k": 5000, "potjans_77k": 1000, "potjans_77k_poisson": 1000,
                      "potjans_8k": 2000, "synapses_only_sparse": 1000, "synapses_only_dense": 1000,
                      "synapses_only_highrate": 500}
 
@@ -553,6 +556,8 @@ def _b200_line(args, r, world, hbm_peak, peak_src):
         return None
     steps, warmup = r["steps"], r["warmup"]
     timesteps = r["timesteps"]
+    kw = WORKLOADS[r["workload"]][1]
+    weak = "N" in kw or "N_E" in kw        # models without a size rule are sharded as they are
     bytes_neuron, bytes_event = r["bytes_neuron"], r["bytes_event"]
     # per-GPU roofline (rank 0): the neurons it owns and the synaptic events it delivered
     n_owned = r["n_neurons"] / (1 if (args.replicas or world == 1) else world)
@@ -563,13 +568,15 @@ def _b200_line(args, r, world, hbm_peak, peak_src):
         "metric": "synaptic_events_per_s", "value": events / dev_s, "unit": "events/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / steps,
         "ms_per_run_rank0": r["per_run_ms"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": _config(r["workload"], r["n_neurons"], n_syn, r["sharded"]),
         "timesteps_per_step": r["sim_steps"],
         "parallelism": "1 GPU" if world == 1 else (
             f"{world} independent replicas (one per GPU)" if args.replicas else
-            f"one network of {world}x the neurons (same synapses per neuron) partitioned by postsynaptic "
-            f"neuron over {world} GPUs; spike lists exchanged by NVLink peer stores inside the persistent kernel"),
+            (f"one network of {world}x the neurons (same synapses per neuron)" if weak else
+             "the same network (fixed size: strong scaling)") +
+            f" partitioned by postsynaptic neuron over {world} GPUs; spike lists exchanged by NVLink peer "
+            f"stores inside the persistent kernel"),
         "execution": ("persistent cooperative step kernel" if r["persistent"] else "one launch per code object")
                      + f", {r['grid']} CTAs x 512 threads",
         "host_seconds": {"codegen_and_build": round(r["build_seconds"], 1), "device_run_call": round(r["run_wall"], 1),
