@@ -409,6 +409,25 @@ def test_sharded_connect_kernels_compile(brian):
     assert not os.path.exists(os.path.join(directory, "code_objects", "sc_cond_synapses_create_generator_codeobject.cpp"))
 
 
+def _run_host_cpp(tmp_path, source):
+    exe = str(tmp_path / os.path.splitext(source)[0])
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "brian2_b200", "csrc"),
+                           "-I", os.path.join(cuda_home, "include"),
+                           os.path.join(ROOT, "tests", "cuda", source), "-o", exe,
+                           "-L", os.path.join(cuda_home, "lib64"), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+def test_per_synapse_host_rng_is_a_function_of_the_synapse(tmp_path):
+    """`b200::SynapseRng` (csrc/b200_synrng.h, sharded construction): `rand()`/`randn()` in an
+    expression assigned to a synaptic variable give a synapse the same value on every rank layout
+    (whole network in one array, or split by postsynaptic neuron), duplicates of a (pre, post)
+    pair draw different numbers, and the draws have the right moments."""
+    out = _run_host_cpp(tmp_path, "synrng_test.cpp")
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout + out.stderr
+
+
 def test_forward_csr_layout_on_the_host(tmp_path):
     """`b200::Pathway::build_forward_csr` (csrc/b200_host.h): the (source, delay bin) layout of the
     forward delivery, checked on the CPU against a brute-force grouping of random synapses (with
@@ -421,3 +440,22 @@ def test_forward_csr_layout_on_the_host(tmp_path):
                            "-L", os.path.join(cuda_home, "lib64"), "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout + out.stderr
+
+
+def test_rebuilt_library_in_the_same_directory_is_not_the_stale_one(brian):
+    """glibc hands back the already loaded object when a path is dlopen()ed again, even if the
+    file was rebuilt in between -- the second simulation would silently run the first model's code.
+    `B200Library` therefore loads a private copy for every path it has loaded before."""
+    import __graft_entry__ as ge
+    from brian2_b200.capi import B200Library
+
+    directory = os.path.join(ge.PREBUILT, "cpu_rebuild")
+    ge.build_project("cuba_1000", directory=directory)
+    first = B200Library(os.path.join(directory, "libb200_project.so"))
+    assert first.lib.b200_get_array_size(b"cuba_P.v") == 1000 * 8
+    ge.build_project("synapses_only", directory=directory)        # another model, same path
+    second = B200Library(os.path.join(directory, "libb200_project.so"))
+    assert second.path != first.path
+    assert second.lib.b200_get_array_size(b"cuba_P.v") == -1
+    assert second.lib.b200_get_array_size(b"so_targets.w") == 2000 * 8
+    assert first.lib.b200_get_array_size(b"cuba_P.v") == 1000 * 8   # the first handle is untouched
