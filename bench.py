@@ -21,7 +21,6 @@ loop inside the persistent kernel, download of the written arrays.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import tempfile
 import threading

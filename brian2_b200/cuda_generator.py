@@ -24,13 +24,13 @@ lookup, and changes what a GPU needs changed:
 """
 import re
 
-from brian2.codegen.generators.cpp_generator import CPPCodeGenerator, c_data_type
+from brian2.codegen.generators.cpp_generator import CPPCodeGenerator
 from brian2.codegen.permutation_analysis import (
     OrderDependenceError,
     check_for_order_independence,
 )
 from brian2.codegen.statements import Statement
-from brian2.core.clocks import BaseClock, Clock  # noqa: F401
+from brian2.core.clocks import BaseClock
 from brian2.core.preferences import prefs
 from brian2.parsing.rendering import CPPNodeRenderer
 from brian2.core.functions import Function

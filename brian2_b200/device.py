@@ -18,8 +18,6 @@ cache, ``main_queue``, run-argument handling, result files.  What is new:
 import os
 import shutil
 import sys
-import tempfile
-import time
 from collections import defaultdict
 
 import numpy as np

@@ -12,7 +12,6 @@ genuine failures."""
 import argparse
 import json
 import os
-import re
 import sys
 import xml.etree.ElementTree as ET
 
