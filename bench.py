@@ -292,6 +292,7 @@ def run_b200(args, rank, world, workload=None, steps=None, warmup=None, sim_step
     b.prefs["devices.b200.multi_gpu"] = not args.replicas
     b.prefs["devices.b200.persistent"] = not args.stepwise
     b.prefs["devices.b200.profile_phases"] = bool(args.phases)
+    b.prefs["devices.b200.libm"] = args.libm
     if args.ctas_per_sm:
         b.prefs["devices.b200.ctas_per_sm"] = args.ctas_per_sm
     if args.grid:
@@ -423,9 +424,50 @@ def parity_prefix_vs_reference(args, r, n_check=200):
         n = min(len(i_dev), len(i_ref))
         bad = np.nonzero((i_dev[:n] != i_ref[:n]) | (t_dev[:n] != t_ref[:n]))[0]
         first_diff = float(t_ref[bad[0]]) if len(bad) else float(min(t_dev[n - 1] if n else 0.0, t_ref[n - 1] if n else 0.0))
-    return {"checked": True, "identical": same, "timesteps": n_check, "spikes_compared": int(len(i_ref)),
-            "against": "the reference's cpp_standalone (serial, -O3 -ffp-contract=off) on the same network, "
-                       "same seed: spike trains (i, t) of the first timesteps", "first_difference_t": first_diff}
+    out = {"checked": True, "identical": same, "timesteps": n_check, "spikes_compared": int(len(i_ref)),
+           "against": "the reference's cpp_standalone (serial, -O3 -ffp-contract=off) on the same network, "
+                      "same seed: spike trains (i, t) of the first timesteps", "first_difference_t": first_diff}
+    try:
+        out["state_check"] = state_bits_vs_reference(args, r["workload"], ref["objs"], n_check)
+    except Exception as ex:   # never hide the measurement
+        out["state_check"] = {"checked": False, "why": f"{type(ex).__name__}: {ex}"}
+    return out
+
+
+def state_bits_vs_reference(args, workload, ref_objs, n_check):
+    """The same `n_check` timesteps once more on the device with `prefs.devices.b200.libm = 'glibc'`
+    (exp / expm1 / pow with the arithmetic of the host's glibc, csrc/b200_glibc_math.cuh): every
+    state variable of every neuron must then have the bits of the reference's cpp_standalone run
+    (`ref_objs`: the strict, serial run of `parity_prefix_vs_reference`)."""
+    import numpy as np
+
+    b = _import_brian()
+    directory = _project_dir(f"bench_state_{workload}", 0)
+    b.prefs["devices.b200.multi_gpu"] = False
+    b.prefs["devices.b200.libm"] = "glibc"
+    _apply_prefs(b, workload)
+    try:
+        objs = _build_script(b, workload, "b200", directory, n_check, 1)
+        b.device.build(directory=directory, compile=True, run=True, with_output=False)
+    finally:
+        b.prefs["devices.b200.libm"] = "cuda"
+        b.prefs["devices.b200.multi_gpu"] = not args.replicas
+        _apply_prefs(b, workload, reset=True)
+    report = {"checked": True, "libm": "glibc", "timesteps": n_check, "variables": {}}
+    ok = True
+    for group, var in objs["state"]:
+        dev = np.ascontiguousarray(getattr(objs[group], var + "_")[:], dtype=np.float64)
+        ref = np.ascontiguousarray(getattr(ref_objs[group], var + "_")[:], dtype=np.float64)
+        differ = int((dev.view(np.uint64) != ref.view(np.uint64)).sum()) if dev.shape == ref.shape else dev.size
+        report["variables"][f"{group}.{var}"] = {"values": int(dev.size), "not_bit_identical": differ}
+        ok = ok and differ == 0
+    mon, mon_ref = objs.get("spikes"), ref_objs.get("spikes")
+    if mon is not None and mon_ref is not None:
+        ok = ok and np.array_equal(np.asarray(mon.i[:]), np.asarray(mon_ref.i[:])) \
+            and np.array_equal(np.asarray(mon.t_[:]), np.asarray(mon_ref.t_[:]))
+    report["bit_identical"] = bool(ok)
+    report["against"] = "final state of every neuron after the same timesteps on cpp_standalone (and its spike train)"
+    return report
 
 
 def parity_multi_gpu(args, rank, world):
@@ -577,7 +619,9 @@ def _b200_line(args, r, world, hbm_peak, peak_src):
             f" partitioned by postsynaptic neuron over {world} GPUs; spike lists exchanged by NVLink peer "
             f"stores inside the persistent kernel"),
         "execution": ("persistent cooperative step kernel" if r["persistent"] else "one launch per code object")
-                     + f", {r['grid']} CTAs x 512 threads",
+                     + f", {r['grid']} CTAs x 512 threads"
+                     + ("; exp/expm1/pow with the host glibc's arithmetic (prefs.devices.b200.libm = 'glibc')"
+                        if args.libm == "glibc" else ""),
         "host_seconds": {"codegen_and_build": round(r["build_seconds"], 1), "device_run_call": round(r["run_wall"], 1),
                          "synapse_creation_on_device": round(r["connect_seconds"], 3),
                          "pathway_csr_build": round(r["prepare_seconds"], 2)},
@@ -618,11 +662,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true",
                     help="default run: skip the extra configurations (Brunel) and the parity checks")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="default run: keep the parity checks, skip the extra configurations (Brunel)")
     ap.add_argument("--replicas", action="store_true",
                     help="N>1: every rank simulates its own copy of the network instead of sharding one "
                          "N-times larger network over the ranks")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning aid: prefs.devices.b200.ctas_per_sm")
     ap.add_argument("--grid", type=int, default=0, help="tuning aid: prefs.devices.b200.grid (max CTAs)")
+    ap.add_argument("--libm", default="cuda", choices=["cuda", "glibc"],
+                    help="prefs.devices.b200.libm: arithmetic of the device's exp/expm1/pow (glibc = bit-identical "
+                         "state, slower state update)")
     ap.add_argument("--phases", action="store_true",
                     help="profiling aid: per-code-object cycle counters inside the persistent kernel")
     ap.add_argument("--stepwise", action="store_true",
@@ -668,7 +717,7 @@ def main():
             parity = parity_prefix_vs_reference(args, r) if world == 1 else parity_multi_gpu(args, rank, world)
         except Exception as ex:   # a failed check must be visible, never hide the measurement
             parity = {"checked": False, "why": f"{type(ex).__name__}: {ex}"}
-        for name in EXTRA_CONFIGS:
+        for name in ([] if args.no_configs else EXTRA_CONFIGS):
             try:
                 rx = run_b200(args, rank, world, workload=name, steps=min(args.steps, 10), warmup=min(args.warmup, 3))
                 extra = _b200_line(args, rx, world, hbm_peak, peak_src)

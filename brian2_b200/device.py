@@ -112,6 +112,19 @@ prefs.register_preferences(
         (the reference's glibc result is, too); the fused form costs a third.
         """,
     ),
+    libm=BrianPreference(
+        default="cuda",
+        validator=lambda v: v in ("cuda", "glibc"),
+        docs="""
+        Arithmetic of ``exp``, ``expm1`` (``exprel``) and ``pow`` in double-precision device code.
+        ``'cuda'``: CUDA's algorithms (<= 1 ulp from the host's glibc; state variables of a
+        Hodgkin-Huxley network agree with ``cpp_standalone`` to rtol 1e-9, spikes are identical).
+        ``'glibc'``: the algorithms of the host's glibc, operation by operation, with the lookup
+        tables read from the host's libm (`brian2_b200.libm_tables`, csrc/b200_glibc_math.cuh):
+        results of these functions -- and with them the state variables -- are bit-identical to a
+        ``cpp_standalone`` build compiled with ``-ffp-contract=off``.  Disables ``fuse_exp_pow``.
+        """,
+    ),
     cse=BrianPreference(
         default=True,
         docs="""
@@ -1217,6 +1230,11 @@ class B200Device(CPPStandaloneDevice):
                 writer.header_files.add(fname)
         shutil.copy2(os.path.join(INCLUDE_DIR, "brian2_b200.h"), os.path.join(directory, "brian2_b200.h"))
         writer.header_files.add("brian2_b200.h")
+        if prefs.devices.b200.libm == "glibc":
+            from . import libm_tables
+
+            libm_tables.write_header(directory)
+            writer.header_files.add("b200_libm_tables.h")
 
     @property
     def library_name(self):
@@ -1230,6 +1248,8 @@ class B200Device(CPPStandaloneDevice):
             flags.append("-DB200_FLOAT32")
         if prefs.devices.b200.csr_l2_evict_last:
             flags.append("-DB200_CSR_EVICT_LAST")
+        if prefs.devices.b200.libm == "glibc":
+            flags.append("-DB200_GLIBC_MATH")
         return " ".join(flags)
 
     def generate_makefile(self, writer, compiler, compiler_flags, linker_flags, nb_threads, debug):

@@ -32,6 +32,10 @@ CASES = {
     # one biological second of the Hodgkin-Huxley network: how long does the device (CUDA exp /
     # expm1, <= 1-2 ulp from glibc) stay spike-exact?  (spike train only)
     "cobahh_1000_long": ("cobahh", dict(N=1000, duration=1.0, trace=())),
+    # one biological second of COBAHH-4000 for `prefs.devices.b200.libm = 'glibc'` (device exp /
+    # expm1 / pow with glibc's arithmetic): final state of every neuron, spike counts and a digest
+    # of the spike train (136 k spikes) -- everything must be bit-identical
+    "cobahh_4000_1s": ("cobahh", dict(N=4000, duration=1.0, trace=())),
     "brunel_hetero": ("brunel", dict(N_E=800, epsilon=0.1, duration=0.1, hetero_delays=True)),
     "brunel_homog": ("brunel", dict(N_E=800, epsilon=0.1, duration=0.1, hetero_delays=False)),
     "stdp_1000": ("stdp", dict(N=1000, duration=0.2)),
@@ -67,6 +71,18 @@ CASES = {
 STOCHASTIC = {"poisson_drive", "poissonfn"}
 
 
+def reduce_train(res):
+    """Replace the spike train (i, t) by its length and SHA-256 digests (small fixture)."""
+    import hashlib
+
+    out = {k: v for k, v in res.items() if k not in ("spikes_i", "spikes_t")}
+    out["spikes_n"] = np.array([len(res["spikes_i"])], dtype=np.int64)
+    for key in ("spikes_i", "spikes_t"):
+        digest = hashlib.sha256(np.ascontiguousarray(res[key]).tobytes()).digest()
+        out[key + "_sha256"] = np.frombuffer(digest, dtype=np.uint8).copy()
+    return out
+
+
 def main(argv):
     names = argv or list(CASES)
     for case in names:
@@ -76,6 +92,8 @@ def main(argv):
         res = {k: v for k, v in res.items() if k != "last_run_time"}
         if case.endswith("_long"):
             res = {k: v for k, v in res.items() if k in ("spikes_i", "spikes_t")}
+        if case.endswith("_1s"):   # state + counts + digest of the train instead of the train
+            res = reduce_train(res)
         if case in STOCHASTIC:   # statistics only
             res = {k: v for k, v in res.items() if not k.endswith(("_i", "_t"))}
         path = os.path.join(HERE, f"{case}.npz")

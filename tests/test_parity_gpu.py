@@ -103,6 +103,45 @@ def test_cobahh_spike_exact_horizon(brian, project_dir):
     assert abs(len(ri) - len(gi)) <= 0.02 * len(gi), (len(ri), len(gi))
 
 
+def _run_with_glibc_math(brian, project_dir, case):
+    model, kwds = CASES[case]
+    try:
+        return models.run_model(brian, model, "b200", project_dir,
+                                prefs_update={"devices.b200.libm": "glibc"}, **kwds)
+    finally:
+        brian.prefs["devices.b200.libm"] = "cuda"
+
+
+def test_cobahh_state_bit_exact_with_glibc_math(brian, project_dir):
+    """`prefs.devices.b200.libm = 'glibc'`: exp / expm1 / pow of the device are glibc's algorithms
+    operation by operation (csrc/b200_glibc_math.cuh; bit-identity of the functions themselves:
+    tests/test_glibc_math_cpu.py), so the Hodgkin-Huxley network is no longer "within rtol 1e-9":
+    every state variable of every neuron, the recorded voltage traces and the spike train are
+    bit-identical to the reference's cpp_standalone run."""
+    objs, res = _run_with_glibc_math(brian, project_dir, "cobahh_1000")
+    _check("cobahh_1000", res, True)
+
+
+def test_cobahh_4000_one_second_bit_exact_with_glibc_math(brian, project_dir):
+    """One biological second (10 000 steps) of COBAHH-4000 -- a chaotic recurrent network, any
+    1-ulp difference in a rate function grows until the trains separate: the final v, m, n, h, ge,
+    gi of all 4000 neurons are bit-identical to the reference's, and so are all 136 k spikes
+    (per-neuron counts and SHA-256 of the (i, t) arrays; the fixture holds digests, not the train)."""
+    import hashlib
+
+    objs, res = _run_with_glibc_math(brian, project_dir, "cobahh_4000_1s")
+    gold = np.load(os.path.join(GOLDEN, "cobahh_4000_1s.npz"))
+    assert len(res["spikes_i"]) == int(gold["spikes_n"][0]), (len(res["spikes_i"]), int(gold["spikes_n"][0]))
+    assert np.array_equal(res["spikes_count"], gold["spikes_count"])
+    for key in ("spikes_i", "spikes_t"):
+        digest = hashlib.sha256(np.ascontiguousarray(res[key]).tobytes()).digest()
+        assert digest == gold[key + "_sha256"].tobytes(), f"{key}: spike train differs from the reference"
+    for key in ("P_v", "P_m", "P_n", "P_h", "P_ge", "P_gi"):
+        same = gold[key].view(np.uint64) == res[key].view(np.uint64)
+        assert same.all(), (f"{key}: {int((~same).sum())} of {same.size} values not bit-identical, "
+                            f"max rel. difference {np.max(np.abs(res[key] - gold[key]) / np.abs(gold[key])):.3g}")
+
+
 def test_in_loop_random_numbers_statistics(brian, project_dir):
     """PoissonInput (binomial sampler) + PoissonGroup on the device's Philox streams: the reference
     disclaims cross-target reproducibility of random numbers (docs_sphinx/advanced/random.rst:28-39),
