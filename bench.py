@@ -428,17 +428,21 @@ def parity_prefix_vs_reference(args, r, n_check=200):
            "against": "the reference's cpp_standalone (serial, -O3 -ffp-contract=off) on the same network, "
                       "same seed: spike trains (i, t) of the first timesteps", "first_difference_t": first_diff}
     try:
-        out["state_check"] = state_bits_vs_reference(args, r["workload"], ref["objs"], n_check)
+        # the reference's arrays must be read while its device is still the active one
+        ref_state = {(g, v): np.array(getattr(ref["objs"][g], v + "_")[:], dtype=np.float64)
+                     for g, v in ref["objs"]["state"]}
+        out["state_check"] = state_bits_vs_reference(args, r["workload"], ref_state, (i_ref, t_ref), n_check)
     except Exception as ex:   # never hide the measurement
         out["state_check"] = {"checked": False, "why": f"{type(ex).__name__}: {ex}"}
     return out
 
 
-def state_bits_vs_reference(args, workload, ref_objs, n_check):
+def state_bits_vs_reference(args, workload, ref_state, ref_train, n_check):
     """The same `n_check` timesteps once more on the device with `prefs.devices.b200.libm = 'glibc'`
     (exp / expm1 / pow with the arithmetic of the host's glibc, csrc/b200_glibc_math.cuh): every
     state variable of every neuron must then have the bits of the reference's cpp_standalone run
-    (`ref_objs`: the strict, serial run of `parity_prefix_vs_reference`)."""
+    (`ref_state`, `ref_train`: final state and spike train of the strict, serial run of
+    `parity_prefix_vs_reference`)."""
     import numpy as np
 
     b = _import_brian()
@@ -457,14 +461,16 @@ def state_bits_vs_reference(args, workload, ref_objs, n_check):
     ok = True
     for group, var in objs["state"]:
         dev = np.ascontiguousarray(getattr(objs[group], var + "_")[:], dtype=np.float64)
-        ref = np.ascontiguousarray(getattr(ref_objs[group], var + "_")[:], dtype=np.float64)
+        ref = ref_state[(group, var)]
         differ = int((dev.view(np.uint64) != ref.view(np.uint64)).sum()) if dev.shape == ref.shape else dev.size
         report["variables"][f"{group}.{var}"] = {"values": int(dev.size), "not_bit_identical": differ}
         ok = ok and differ == 0
-    mon, mon_ref = objs.get("spikes"), ref_objs.get("spikes")
-    if mon is not None and mon_ref is not None:
-        ok = ok and np.array_equal(np.asarray(mon.i[:]), np.asarray(mon_ref.i[:])) \
-            and np.array_equal(np.asarray(mon.t_[:]), np.asarray(mon_ref.t_[:]))
+    mon = objs.get("spikes")
+    if mon is not None:
+        train_same = bool(np.array_equal(np.asarray(mon.i[:]), ref_train[0])
+                          and np.array_equal(np.asarray(mon.t_[:]), ref_train[1]))
+        report["spike_train_identical"] = train_same
+        ok = ok and train_same
     report["bit_identical"] = bool(ok)
     report["against"] = "final state of every neuron after the same timesteps on cpp_standalone (and its spike train)"
     return report
