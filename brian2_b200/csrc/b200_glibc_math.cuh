@@ -1,13 +1,13 @@
-// b200_glibc_math.cuh -- exp / expm1 / pow with the arithmetic of the host's glibc, for device code.
+// b200_glibc_math.cuh -- exp / expm1 / log / pow with the arithmetic of the host's glibc, for device code.
 //
-// Why: the oracle of this path is the reference's cpp_standalone build, whose exp()/expm1()/pow()
+// Why: the oracle of this path is the reference's cpp_standalone build, whose exp()/expm1()/log()/pow()
 // are glibc's.  CUDA's functions differ from them by <= 1 ulp in a few per cent of the arguments,
 // which is enough to leave Hodgkin-Huxley state variables only "within rtol" of the oracle.  With
 // `prefs.devices.b200.libm = 'glibc'` (-DB200_GLIBC_MATH) the device runs the functions below
 // instead: every floating-point operation -- including which a*b+c are fused -- is the one the
-// x86-64 FMA variants of glibc 2.39 execute (`__exp_fma`, `__pow_fma`: the table-driven
-// algorithms of sysdeps/ieee754/dbl-64/e_exp.c, e_pow.c; `__expm1_fma`: the fdlibm algorithm of
-// s_expm1.c), so the results are bit-identical for every argument.  The two lookup tables and the
+// x86-64 FMA variants of glibc 2.39 execute (`__exp_fma`, `__log_fma`, `__pow_fma`: the table-driven
+// algorithms of sysdeps/ieee754/dbl-64/e_exp.c, e_log.c, e_pow.c; `__expm1_fma`: the fdlibm algorithm of
+// s_expm1.c), so the results are bit-identical for every argument.  The three lookup tables and the
 // polynomial coefficients come from the host's libm itself (b200_libm_tables.h, written into the
 // project by brian2_b200/libm_tables.py).  tests/cuda/glibc_math_test.cpp compiles this header for
 // the host and compares it with the real functions over >= 10^7 arguments per function.
@@ -49,6 +49,7 @@ namespace b200g {
 
 B200G_TABLE uint64_t kExpTab[256] = {B200_LIBM_EXP_TAB};        // {error term, value - (i << 45)} x 128
 B200G_TABLE uint64_t kPowLogTab[384] = {B200_LIBM_POW_TAB};     // {1/c, log(c) high, log(c) low} x 128
+B200G_TABLE uint64_t kLogTab[256] = {B200_LIBM_LOG_TAB};        // {1/c, log(c)} x 128
 
 static const uint64_t kInfBits = 0x7ff0000000000000ull;
 static const uint64_t kOneBits = 0x3ff0000000000000ull;
@@ -185,6 +186,57 @@ B200G_FN double expm1(double x) {
     const uint64_t yb = B200G_BITS(y);
     const uint32_t high = (uint32_t)(yb >> 32) + (uint32_t)(k << 20);
     return B200G_DBL(((uint64_t)high << 32) | (yb & 0xffffffffull));
+}
+
+// sysdeps/ieee754/dbl-64/e_log.c (__log), FMA variant.
+B200G_SLOW double log_near_one(double x) {                 // 1 - 2^-4 <= x < 1 + 0x1.09p-4
+    if (B200G_BITS(x) == kOneBits) return 0.0;
+    const double r = B200G_SUB(x, 1.0);
+    const double r2 = B200G_MUL(r, r);
+    const double r3 = B200G_MUL(r, r2);
+    const double a = B200G_FMA(r2, B200_LIBM_LOG_B3, B200G_FMA(r, B200_LIBM_LOG_B2, B200_LIBM_LOG_B1));
+    const double b = B200G_FMA(r2, B200_LIBM_LOG_B6, B200G_FMA(r, B200_LIBM_LOG_B5, B200_LIBM_LOG_B4));
+    double c = B200G_FMA(r2, B200_LIBM_LOG_B9, B200G_FMA(r, B200_LIBM_LOG_B8, B200_LIBM_LOG_B7));
+    c = B200G_FMA(r3, B200_LIBM_LOG_B10, c);
+    const double e = B200G_FMA(B200G_FMA(c, r3, b), r3, a);
+    // r*r*B0 with the high part of r (27 bits, so rhi*rhi is exact), both roundings fused away
+    const double t = B200G_FMA(r, 0x1p27, r);
+    const double rhi = B200G_FMA(-0x1p27, r, t);
+    const double rlo = B200G_SUB(r, rhi);
+    const double rhi2 = B200G_MUL(rhi, rhi);
+    const double hi = B200G_FMA(rhi2, B200_LIBM_LOG_B0, r);
+    double lo = B200G_FMA(rhi2, B200_LIBM_LOG_B0, B200G_SUB(r, hi));
+    lo = B200G_FMA(B200G_MUL(B200_LIBM_LOG_B0, rlo), B200G_ADD(r, rhi), lo);
+    return B200G_ADD(hi, B200G_FMA(e, r3, lo));
+}
+B200G_FN double log(double x) {
+    uint64_t ix = B200G_BITS(x);
+    const uint32_t top = (uint32_t)(ix >> 48);
+    if (ix - 0x3fee000000000000ull < 0x0003090000000000ull) return log_near_one(x);
+    if (top - 0x0010u >= 0x7ff0u - 0x0010u) {              // x < 2^-1022, inf or nan
+        if (ix * 2 == 0) return B200G_DBL(kInfBits | kSignBit);
+        if (ix == kInfBits) return x;
+        if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return B200G_DBL(0x7ff8000000000000ull | kSignBit);
+        ix = B200G_BITS(B200G_MUL(x, 0x1p52));             // subnormal: normalise
+        ix -= 52ull << 52;
+    }
+    const uint64_t tmp = ix - 0x3fe6000000000000ull;
+    const uint32_t i = (uint32_t)(tmp >> 45) & 127u;
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = B200G_DBL(ix - (tmp & 0xfff0000000000000ull));
+    const double invc = B200G_DBL(kLogTab[2 * i]);
+    const double logc = B200G_DBL(kLogTab[2 * i + 1]);
+    const double r = B200G_FMA(z, invc, -1.0);
+    const double kd = (double)k;
+    const double w = B200G_FMA(kd, B200_LIBM_LOG_LN2HI, logc);
+    const double hi = B200G_ADD(w, r);
+    const double lo = B200G_FMA(kd, B200_LIBM_LOG_LN2LO, B200G_ADD(B200G_SUB(w, hi), r));
+    const double r2 = B200G_MUL(r, r);
+    const double p12 = B200G_FMA(r, B200_LIBM_LOG_A2, B200_LIBM_LOG_A1);
+    const double p34 = B200G_FMA(r, B200_LIBM_LOG_A4, B200_LIBM_LOG_A3);
+    const double q = B200G_FMA(p34, r2, p12);
+    const double y = B200G_FMA(B200G_MUL(r, r2), q, B200G_FMA(r2, B200_LIBM_LOG_A0, lo));
+    return B200G_ADD(y, hi);
 }
 
 // ---- pow: sysdeps/ieee754/dbl-64/e_pow.c (__pow), FMA variant ---------------------------------

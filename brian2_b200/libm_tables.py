@@ -2,18 +2,19 @@
 Constants and lookup tables of the host's glibc ``exp`` / ``pow``, read from the libm binary the
 reference's ``cpp_standalone`` build links against.
 
-``prefs.devices.b200.libm = 'glibc'`` makes the device evaluate ``exp``, ``expm1`` and ``pow`` with
+``prefs.devices.b200.libm = 'glibc'`` makes the device evaluate ``exp``, ``expm1``, ``log`` and ``pow`` with
 the arithmetic of the host's libm (csrc/b200_glibc_math.cuh), so that state variables are
 bit-identical to a ``cpp_standalone`` run -- the oracle of this path.
-glibc >= 2.28 computes exp/pow from two small tables (``__exp_data``: 2^(i/128) as value + error
-term; ``__pow_log_data``: 1/c, log(c) in two pieces for 128 subintervals of [0.71, 1.42)) whose
+glibc >= 2.28 computes exp/pow/log from small tables (``__exp_data``: 2^(i/128) as value + error
+term; ``__pow_log_data``: 1/c, log(c) in two pieces for 128 subintervals of [0.71, 1.42);
+``__log_data``: 1/c, log(c) for 128 subintervals of [0.69, 1.38)) whose
 entries were chosen by a search, not by a closed formula, so they cannot be recomputed here: they
 are looked up in the ``.rodata`` of the very library the oracle calls, by content (each table
 follows a run of constants with known values), checked structurally, and written into the
 project directory as ``b200_libm_tables.h``.  Nothing of glibc is stored in this repository.
 
 The x86-64 build of glibc selects its functions at load time; with FMA and AVX2 (every host this
-package targets) the ``__exp_fma/__pow_fma/__expm1_fma`` variants run, whose contraction of
+package targets) the ``__exp_fma/__pow_fma/__log_fma/__expm1_fma`` variants run, whose contraction of
 ``a*b+c`` into fused operations is restated operation by operation in b200_glibc_math.cuh.
 ``tests/cuda/glibc_math_test.cpp`` compiles that header for the host and compares it bit by bit
 with the real functions (tests/test_glibc_math_cpu.py).
@@ -84,8 +85,8 @@ def _rodata(path):
     raise RuntimeError(f"{path}: no .rodata section")
 
 
-def _find_run(data, values, what):
-    """Offset of the unique 8-byte aligned occurrence of the doubles `values` in `data`."""
+def _find_all(data, values):
+    """Offsets of all 8-byte aligned occurrences of the doubles `values` in `data`."""
     pattern = b"".join(struct.pack("<d", v) for v in values)
     hits = []
     pos = data.find(pattern)
@@ -93,6 +94,12 @@ def _find_run(data, values, what):
         if pos % 8 == 0:
             hits.append(pos)
         pos = data.find(pattern, pos + 1)
+    return hits
+
+
+def _find_run(data, values, what):
+    """Offset of the unique 8-byte aligned occurrence of the doubles `values` in `data`."""
+    hits = _find_all(data, values)
     if len(hits) != 1:
         raise RuntimeError(f"libm: {what} found {len(hits)} times (expected once); unsupported glibc build")
     return hits[0]
@@ -103,7 +110,8 @@ def read_tables(path=None):
 
     Returns a dict: ``exp_k`` (InvLn2N, Shift, NegLn2hiN, NegLn2loN, C2..C5 as doubles), ``exp_tab``
     (256 uint64: error term, scaled value per entry), ``pow_k`` (Ln2hi, Ln2lo, A0..A6), ``pow_tab``
-    (128 x (invc, logc, logctail) as uint64), ``path``.
+    (128 x (invc, logc, logctail) as uint64), ``log_k`` (Ln2hi, Ln2lo, A0..A4, B0..B10), ``log_tab``
+    (128 x (invc, logc) as uint64), ``path``.
     """
     path = path or find_libm()
     data, _ = _rodata(path)
@@ -152,7 +160,26 @@ def read_tables(path=None):
             raise RuntimeError(f"libm: pow-log table entry {i} fails its check")
         raw = u64(ptab + 32 * i, 4)
         pow_tab += [raw[0], raw[2], raw[3]]
-    return {"exp_k": exp_k, "exp_tab": exp_tab, "pow_k": pow_k, "pow_tab": pow_tab, "path": path}
+
+    # ---- __log_data: {ln2hi, ln2lo, poly[5], poly1[11], tab[N]{invc, logc}, ...} --------------
+    # same ln2 split as pow; told apart by poly[0] = -0.5 - 1 ulp and poly1[0] = -0.5 exactly
+    a0 = float.fromhex("-0x1.0000000000001p-1")
+    lbase = [h for h in _find_all(data, [ln2hi, ln2lo, a0]) if f64(h + 7 * 8, 1)[0] == -0.5]
+    if len(lbase) != 1:
+        raise RuntimeError(f"libm: log constants found {len(lbase)} times (expected once)")
+    lbase = lbase[0]
+    log_k = f64(lbase, 18)            # ln2hi, ln2lo, A0..A4, B0..B10
+    if not (abs(log_k[3] - 1 / 3) < 1e-9 and abs(log_k[8] - 1 / 3) < 1e-12 and abs(log_k[17] + 1 / 12) < 1e-3):
+        raise RuntimeError("libm: unexpected layout of the log constants")
+    ltab = lbase + 18 * 8
+    log_tab = []
+    for i in range(_N):
+        invc, logc = f64(ltab + 16 * i, 2)
+        if not (0.68 < invc < 1.46 and abs(logc + math.log(invc)) < 1e-13):
+            raise RuntimeError(f"libm: log table entry {i} fails its check")
+        log_tab += u64(ltab + 16 * i, 2)
+    return {"exp_k": exp_k, "exp_tab": exp_tab, "pow_k": pow_k, "pow_tab": pow_tab,
+            "log_k": log_k, "log_tab": log_tab, "path": path}
 
 
 def header_text(tables=None):
@@ -163,14 +190,17 @@ def header_text(tables=None):
         ", ".join(f"0x{v:016x}ull" for v in vals[i:i + 4]) for i in range(0, len(vals), 4))
     names_e = ["INVLN2N", "SHIFT", "NEGLN2HIN", "NEGLN2LON", "C2", "C3", "C4", "C5"]
     names_p = ["LN2HI", "LN2LO", "A0", "A1", "A2", "A3", "A4", "A5", "A6"]
+    names_l = ["LN2HI", "LN2LO"] + [f"A{i}" for i in range(5)] + [f"B{i}" for i in range(11)]
     lines = [
         "// b200_libm_tables.h -- generated by brian2_b200/libm_tables.py from",
-        f"// {t['path']}: the constants and tables of the host libm's exp()/pow(),",
+        f"// {t['path']}: the constants and tables of the host libm's exp()/pow()/log(),",
         "// so that device code reproduces the arithmetic of the oracle's own library.",
         "#pragma once",
     ]
     lines += [f"#define B200_LIBM_EXP_{n} {hexd(v)}" for n, v in zip(names_e, t["exp_k"])]
     lines += [f"#define B200_LIBM_POW_{n} {hexd(v)}" for n, v in zip(names_p, t["pow_k"])]
+    lines += [f"#define B200_LIBM_LOG_{n} {hexd(v)}" for n, v in zip(names_l, t["log_k"])]
+    lines.append("#define B200_LIBM_LOG_TAB \\\n    " + rows(t["log_tab"]))
     lines.append("#define B200_LIBM_EXP_TAB \\\n    " + rows(t["exp_tab"]))
     lines.append("#define B200_LIBM_POW_TAB \\\n    " + rows(t["pow_tab"]))
     return "\n".join(lines) + "\n"

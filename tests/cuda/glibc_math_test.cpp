@@ -1,4 +1,4 @@
-// CPU check of csrc/b200_glibc_math.cuh: the restated exp / expm1 / pow must return the bits of
+// CPU check of csrc/b200_glibc_math.cuh: the restated exp / expm1 / log / pow must return the bits of
 // the host's glibc functions (the arithmetic of the oracle, cpp_standalone) for every argument.
 // Build: g++ -O2 -ffp-contract=off -mfma -I<dir with b200_libm_tables.h> -I<csrc>.
 // Usage: glibc_math_test [arguments per distribution, default 2000000].  Prints one line per
@@ -59,13 +59,16 @@ int main(int argc, char** argv) {
     const long n = argc > 1 ? atol(argv[1]) : 2000000;
     auto my_exp = [](double x) { return b200g::exp(x); };
     auto my_expm1 = [](double x) { return b200g::expm1(x); };
+    auto my_log = [](double x) { return b200g::log(x); };
     auto my_pow = [](double x, double y) { return b200g::pow(x, y); };
     // volatile function pointers: the compiler must call libm, not fold or substitute
     double (*volatile ref_exp)(double) = ::exp;
     double (*volatile ref_expm1)(double) = ::expm1;
+    double (*volatile ref_log)(double) = ::log;
     double (*volatile ref_pow)(double, double) = ::pow;
     auto r_exp = [&](double x) { return ref_exp(x); };
     auto r_expm1 = [&](double x) { return ref_expm1(x); };
+    auto r_log = [&](double x) { return ref_log(x); };
     auto r_pow = [&](double x, double y) { return ref_pow(x, y); };
 
     sweep1("exp  [-20, 5] (HH rates)", n, [] { return uni(-20, 5); }, my_exp, r_exp);
@@ -83,6 +86,13 @@ int main(int argc, char** argv) {
     sweep1("expm1 [10, 16] (k ~ 20)", n / 4, [] { return uni(10, 16); }, my_expm1, r_expm1);
     sweep1("expm1 any bit pattern", n, [] { return anybits(); }, my_expm1, r_expm1);
     sweep1("expm1 tiny", n / 4, [] { return uni(-1, 1) * std::ldexp(1.0, -(int)(rnd() % 80)); }, my_expm1, r_expm1);
+
+    sweep1("log  (0, 100]", n, [] { return uni(0, 100); }, my_log, r_log);
+    sweep1("log  [0.9, 1.1] (near one)", n, [] { return uni(0.9, 1.1); }, my_log, r_log);
+    sweep1("log  [0.93, 0.94], [1.06, 1.07]", n / 4, [] { return (rnd() & 1) ? uni(0.93, 0.94) : uni(1.06, 1.07); }, my_log, r_log);
+    sweep1("log  whole range", n, [] { return std::ldexp(uni(0.5, 1), (int)(rnd() % 2098) - 1074); }, my_log, r_log);
+    sweep1("log  any bit pattern", n, [] { return anybits(); }, my_log, r_log);
+    sweep1("log  1 +- tiny", n / 4, [] { return 1.0 + uni(-1, 1) * std::ldexp(1.0, -(int)(rnd() % 53)); }, my_log, r_log);
 
     sweep2("pow  gate**{3,4}", n, [](double& x, double& y) { x = uni(0, 1); y = 3 + (double)(rnd() & 1); }, my_pow, r_pow);
     sweep2("pow  exp(a)**c (HH rates)", n, [&](double& x, double& y) {

@@ -64,6 +64,9 @@ CASES = {
     "multiclock": ("multiclock", dict(N=200, duration=0.05)),
     "sharedvar": ("sharedvar", dict(N=300, duration=0.03)),
     "synstate": ("synstate", dict(N=150, duration=0.03)),
+    # exp / expm1 / exprel / log / pow (+ the powers g++ folds) per neuron and step over wide,
+    # drifting argument ranges: bit-identical with prefs.devices.b200.libm = 'glibc'
+    "mathfuncs": ("mathfuncs", dict(N=4096, duration=0.01)),
 }
 
 

@@ -1,5 +1,5 @@
 """`prefs.devices.b200.libm = 'glibc'` (csrc/b200_glibc_math.cuh, brian2_b200/libm_tables.py):
-the device's exp / expm1 / pow must be the host glibc's functions bit for bit, because the oracle
+the device's exp / expm1 / log / pow must be the host glibc's functions bit for bit, because the oracle
 of this path -- the reference's cpp_standalone build -- calls exactly those.  Everything that can
 be checked without a GPU is checked here: the tables found in the host's libm mean what the
 algorithm assumes, the restated arithmetic (compiled for the host from the same header the device
@@ -32,7 +32,7 @@ def test_tables_of_the_host_libm_mean_what_the_algorithms_assume(tables):
     from brian2_b200.libm_tables import _dbl
 
     mp.mp.prec = 240
-    assert len(tables["exp_tab"]) == 256 and len(tables["pow_tab"]) == 384
+    assert len(tables["exp_tab"]) == 256 and len(tables["pow_tab"]) == 384 and len(tables["log_tab"]) == 256
     for i in range(128):
         H = _dbl(tables["exp_tab"][2 * i + 1] + (i << 45))
         T = _dbl(tables["exp_tab"][2 * i])
@@ -43,6 +43,10 @@ def test_tables_of_the_host_libm_mean_what_the_algorithms_assume(tables):
         invc, logc, tail = (_dbl(v) for v in tables["pow_tab"][3 * i:3 * i + 3])
         assert abs(mp.mpf(logc) + mp.mpf(tail) + mp.log(mp.mpf(invc))) < mp.mpf(2) ** -90, i
         assert tables["pow_tab"][3 * i] & ((1 << 40) - 1) == 0, (i, "1/c must have a short mantissa")
+    for i in range(128):                 # log: (1/c, log c), log c rounded to 2^-43 and c chosen close to it
+        invc, logc = (_dbl(v) for v in tables["log_tab"][2 * i:2 * i + 2])
+        assert abs(mp.mpf(logc) + mp.log(mp.mpf(invc))) < mp.mpf(2) ** -60, i
+        assert mp.mpf(logc) * 2 ** 43 == mp.floor(mp.mpf(logc) * 2 ** 43), i
     # subintervals [c_i (1 - 1/256), c_i (1 + 1/256)) tile [0x1.69555p-1, 0x1.69555p0)
     centres = sorted(1.0 / _dbl(tables["pow_tab"][3 * i]) for i in range(128))
     assert 0.70 < centres[0] < 0.71 and 1.40 < centres[-1] < 1.42
@@ -54,14 +58,14 @@ def test_header_is_self_describing(tables, tmp_path):
     path = libm_tables.write_header(str(tmp_path), tables)
     text = open(path).read()
     assert tables["path"] in text and "#define B200_LIBM_EXP_TAB" in text and "#define B200_LIBM_POW_TAB" in text
-    assert len(re.findall(r"0x[0-9a-f]{16}ull", text)) == 256 + 384
+    assert len(re.findall(r"0x[0-9a-f]{16}ull", text)) == 256 + 384 + 256
     stamp = os.path.getmtime(path)
     libm_tables.write_header(str(tmp_path), tables)          # unchanged content: not rewritten (make)
     assert os.path.getmtime(path) == stamp
 
 
 def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
-    """tests/cuda/glibc_math_test.cpp: 25 argument distributions (Hodgkin-Huxley ranges, whole
+    """tests/cuda/glibc_math_test.cpp: 31 argument distributions (Hodgkin-Huxley ranges, whole
     range, over/underflow, subnormal results, random bit patterns, special values), 4 * 10^6
     arguments each (> 10^7 per function), every result compared with the libm call the
     reference's C++ code makes.  NaNs compare equal to NaNs."""
@@ -75,8 +79,8 @@ def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
     out = subprocess.run([exe, "4000000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
     lines = [l for l in out.stdout.splitlines() if "arguments" in l]
-    assert len(lines) == 25 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
-    for fn in ("exp ", "expm1", "pow "):
+    assert len(lines) == 31 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
+    for fn in ("exp ", "expm1", "log ", "pow "):
         assert sum(int(l.split()[-4]) for l in lines if l.startswith(fn)) > 10 ** 7, fn
 
 
@@ -126,7 +130,7 @@ def test_hodgkin_huxley_project_builds_with_glibc_math(brian):
     assert "sm_100a" in sass
     elf = subprocess.run(["cuobjdump", "-elf", os.path.join(directory, "libb200_project.so")],
                          capture_output=True, text=True).stdout
-    assert "kExpTab" in elf and "kPowLogTab" in elf
+    assert "kExpTab" in elf and "kPowLogTab" in elf and "kLogTab" in elf
     with pytest.raises(Exception):
         b.prefs["devices.b200.libm"] = "fdlibm"
     assert b.prefs["devices.b200.libm"] == "cuda"

@@ -122,6 +122,18 @@ def test_cobahh_state_bit_exact_with_glibc_math(brian, project_dir):
     _check("cobahh_1000", res, True)
 
 
+def test_every_libm_call_bit_exact_with_glibc_math(brian, project_dir):
+    """exp, expm1, exprel, log, pow with run-time and literal exponents (incl. the ones g++ folds:
+    x**2, p**-1) and exp(a)**c, 4096 neurons x 100 steps, arguments over [-30, 30] / (0, 60] /
+    [-6, 6] from chaotic maps that every result perturbs (tests/models.py: mathfuncs): the final
+    state equals the reference's bit for bit only if every single evaluation on the device did."""
+    objs, res = _run_with_glibc_math(brian, project_dir, "mathfuncs")
+    gold = np.load(os.path.join(GOLDEN, "mathfuncs.npz"))
+    for key in gold.files:
+        same = gold[key].view(np.uint64) == res[key].view(np.uint64)
+        assert same.all(), f"mathfuncs:{key}: {int((~same).sum())} of {same.size} values not bit-identical"
+
+
 def test_cobahh_4000_one_second_bit_exact_with_glibc_math(brian, project_dir):
     """One biological second (10 000 steps) of COBAHH-4000 -- a chaotic recurrent network, any
     1-ulp difference in a rate function grows until the trains separate: the final v, m, n, h, ge,
