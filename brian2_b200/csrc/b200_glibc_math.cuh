@@ -239,6 +239,76 @@ B200G_FN double log(double x) {
     return B200G_ADD(y, hi);
 }
 
+// ---- functions glibc builds on the ones above (fdlibm; compiled without fused operations) ------
+// sysdeps/ieee754/dbl-64/s_tanh.c
+B200G_FN double tanh(double x) {
+    const uint64_t ix64 = B200G_BITS(x);
+    const uint32_t ix = (uint32_t)(ix64 >> 32) & 0x7fffffffu;
+    const bool neg = (ix64 >> 63) != 0;
+    if (ix >= 0x7ff00000u)                                 // inf: +-1, nan: nan
+        return neg ? B200G_SUB(B200G_DIV(1.0, x), 1.0) : B200G_ADD(B200G_DIV(1.0, x), 1.0);
+    double z;
+    if (ix < 0x40360000u) {                                // |x| < 22
+        if ((ix64 << 1) == 0) return x;
+        if (ix < 0x3c800000u) return B200G_MUL(x, B200G_ADD(1.0, x));            // |x| < 2^-55
+        const double ax = B200G_DBL(ix64 & ~kSignBit);
+        if (ix >= 0x3ff00000u) {                           // |x| >= 1
+            const double t = expm1(B200G_ADD(ax, ax));
+            z = B200G_SUB(1.0, B200G_DIV(2.0, B200G_ADD(t, 2.0)));
+        } else {
+            const double t = expm1(B200G_MUL(ax, -2.0));
+            z = B200G_DIV(-t, B200G_ADD(t, 2.0));
+        }
+    } else {
+        z = B200G_SUB(1.0, 1e-300);
+    }
+    return neg ? -z : z;
+}
+// sysdeps/ieee754/dbl-64/e_sinh.c
+B200G_FN double sinh(double x) {
+    const uint64_t ix64 = B200G_BITS(x);
+    const uint32_t ix = (uint32_t)(ix64 >> 32) & 0x7fffffffu, lx = (uint32_t)ix64;
+    if (ix >= 0x7ff00000u) return B200G_ADD(x, x);
+    const double h = (ix64 >> 63) ? -0.5 : 0.5;
+    const double ax = B200G_DBL(ix64 & ~kSignBit);
+    if (ix < 0x40360000u) {                                // |x| < 22
+        if (ix < 0x3e300000u) return x;                    // |x| < 2^-28
+        const double t = expm1(ax);
+        if (ix < 0x3ff00000u)
+            return B200G_MUL(h, B200G_SUB(B200G_MUL(2.0, t), B200G_DIV(B200G_MUL(t, t), B200G_ADD(t, 1.0))));
+        return B200G_MUL(h, B200G_ADD(t, B200G_DIV(t, B200G_ADD(t, 1.0))));
+    }
+    if (ix < 0x40862e42u) return B200G_MUL(h, exp(ax));    // |x| < log(DBL_MAX)
+    if (ix < 0x408633ceu || (ix == 0x408633ceu && lx <= 0x8fb9f87du)) {
+        const double w = exp(B200G_MUL(0.5, ax));
+        return B200G_MUL(B200G_MUL(h, w), w);
+    }
+    return B200G_MUL(x, 1.0e307);                          // overflow
+}
+// sysdeps/ieee754/dbl-64/e_cosh.c
+B200G_FN double cosh(double x) {
+    const uint64_t ix64 = B200G_BITS(x);
+    const uint32_t ix = (uint32_t)(ix64 >> 32) & 0x7fffffffu, lx = (uint32_t)ix64;
+    const double ax = B200G_DBL(ix64 & ~kSignBit);
+    if (ix < 0x40360000u) {                                // |x| < 22
+        if (ix < 0x3fd62e43u) {                            // |x| < 0.5 ln2
+            if (ix < 0x3c800000u) return 1.0;
+            const double t = expm1(ax);
+            const double w = B200G_ADD(1.0, t);
+            return B200G_ADD(1.0, B200G_DIV(B200G_MUL(t, t), B200G_ADD(w, w)));
+        }
+        const double t = exp(ax);
+        return B200G_ADD(B200G_MUL(0.5, t), B200G_DIV(0.5, t));
+    }
+    if (ix < 0x40862e42u) return B200G_MUL(0.5, exp(ax));
+    if (ix < 0x408633ceu || (ix == 0x408633ceu && lx <= 0x8fb9f87du)) {
+        const double w = exp(B200G_MUL(0.5, ax));
+        return B200G_MUL(B200G_MUL(0.5, w), w);
+    }
+    if (ix >= 0x7ff00000u) return B200G_MUL(x, x);
+    return B200G_DBL(kInfBits);                            // overflow
+}
+
 // ---- pow: sysdeps/ieee754/dbl-64/e_pow.c (__pow), FMA variant ---------------------------------
 B200G_FN int pow_checkint(uint64_t iy) {                   // 0: not an integer, 1: odd, 2: even
     const int e = (int)(iy >> 52) & 0x7ff;

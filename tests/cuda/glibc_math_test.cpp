@@ -94,6 +94,33 @@ int main(int argc, char** argv) {
     sweep1("log  any bit pattern", n, [] { return anybits(); }, my_log, r_log);
     sweep1("log  1 +- tiny", n / 4, [] { return 1.0 + uni(-1, 1) * std::ldexp(1.0, -(int)(rnd() % 53)); }, my_log, r_log);
 
+    {
+        double (*volatile ref_tanh)(double) = ::tanh;
+        double (*volatile ref_sinh)(double) = ::sinh;
+        double (*volatile ref_cosh)(double) = ::cosh;
+        auto r_tanh = [&](double x) { return ref_tanh(x); };
+        auto r_sinh = [&](double x) { return ref_sinh(x); };
+        auto r_cosh = [&](double x) { return ref_cosh(x); };
+        auto my_tanh = [](double x) { return b200g::tanh(x); };
+        auto my_sinh = [](double x) { return b200g::sinh(x); };
+        auto my_cosh = [](double x) { return b200g::cosh(x); };
+        auto wide = [] { return uni(-1, 1) * std::ldexp(1.0, (int)(rnd() % 70) - 60); };     // 2^-60 .. 2^9
+        sweep1("tanh [-25, 25]", n, [] { return uni(-25, 25); }, my_tanh, r_tanh);
+        sweep1("tanh [-1.2, 1.2]", n, [] { return uni(-1.2, 1.2); }, my_tanh, r_tanh);
+        sweep1("tanh all magnitudes", n / 2, wide, my_tanh, r_tanh);
+        sweep1("tanh any bit pattern", n / 2, [] { return anybits(); }, my_tanh, r_tanh);
+        sweep1("sinh [-25, 25]", n, [] { return uni(-25, 25); }, my_sinh, r_sinh);
+        sweep1("sinh [-1.2, 1.2]", n, [] { return uni(-1.2, 1.2); }, my_sinh, r_sinh);
+        sweep1("sinh [-712, 712]", n / 2, [] { return uni(-712, 712); }, my_sinh, r_sinh);
+        sweep1("sinh all magnitudes", n / 2, wide, my_sinh, r_sinh);
+        sweep1("sinh any bit pattern", n / 2, [] { return anybits(); }, my_sinh, r_sinh);
+        sweep1("cosh [-25, 25]", n, [] { return uni(-25, 25); }, my_cosh, r_cosh);
+        sweep1("cosh [-0.5, 0.5]", n, [] { return uni(-0.5, 0.5); }, my_cosh, r_cosh);
+        sweep1("cosh [-712, 712]", n / 2, [] { return uni(-712, 712); }, my_cosh, r_cosh);
+        sweep1("cosh all magnitudes", n / 2, wide, my_cosh, r_cosh);
+        sweep1("cosh any bit pattern", n / 2, [] { return anybits(); }, my_cosh, r_cosh);
+    }
+
     sweep2("pow  gate**{3,4}", n, [](double& x, double& y) { x = uni(0, 1); y = 3 + (double)(rnd() & 1); }, my_pow, r_pow);
     sweep2("pow  exp(a)**c (HH rates)", n, [&](double& x, double& y) {
         x = ref_exp(uni(-10, 10)); y = (rnd() & 1) ? 0.025 : 0.05555555555555555; }, my_pow, r_pow);

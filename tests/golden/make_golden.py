@@ -66,7 +66,7 @@ CASES = {
     "synstate": ("synstate", dict(N=150, duration=0.03)),
     # exp / expm1 / exprel / log / pow (+ the powers g++ folds) per neuron and step over wide,
     # drifting argument ranges: bit-identical with prefs.devices.b200.libm = 'glibc'
-    "mathfuncs": ("mathfuncs", dict(N=4096, duration=0.01)),
+    "mathfuncs": ("mathfuncs", dict(N=2048, duration=0.01)),
 }
 
 

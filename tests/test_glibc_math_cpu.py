@@ -1,5 +1,5 @@
 """`prefs.devices.b200.libm = 'glibc'` (csrc/b200_glibc_math.cuh, brian2_b200/libm_tables.py):
-the device's exp / expm1 / log / pow must be the host glibc's functions bit for bit, because the oracle
+the device's exp / expm1 / log / pow (and tanh / sinh / cosh) must be the host glibc's functions bit for bit, because the oracle
 of this path -- the reference's cpp_standalone build -- calls exactly those.  Everything that can
 be checked without a GPU is checked here: the tables found in the host's libm mean what the
 algorithm assumes, the restated arithmetic (compiled for the host from the same header the device
@@ -65,7 +65,7 @@ def test_header_is_self_describing(tables, tmp_path):
 
 
 def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
-    """tests/cuda/glibc_math_test.cpp: 31 argument distributions (Hodgkin-Huxley ranges, whole
+    """tests/cuda/glibc_math_test.cpp: 45 argument distributions (Hodgkin-Huxley ranges, whole
     range, over/underflow, subnormal results, random bit patterns, special values), 4 * 10^6
     arguments each (> 10^7 per function), every result compared with the libm call the
     reference's C++ code makes.  NaNs compare equal to NaNs."""
@@ -79,8 +79,8 @@ def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
     out = subprocess.run([exe, "4000000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
     lines = [l for l in out.stdout.splitlines() if "arguments" in l]
-    assert len(lines) == 31 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
-    for fn in ("exp ", "expm1", "log ", "pow "):
+    assert len(lines) == 45 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
+    for fn in ("exp ", "expm1", "log ", "pow ", "tanh", "sinh", "cosh"):
         assert sum(int(l.split()[-4]) for l in lines if l.startswith(fn)) > 10 ** 7, fn
 
 
