@@ -30,6 +30,7 @@
 #define B200G_BITS(x) ((uint64_t)__double_as_longlong(x))
 #define B200G_DBL(u) __longlong_as_double((long long)(u))
 #else   // host build of the test harness (g++ -ffp-contract=off)
+#include <math.h>
 #include <string.h>
 #define B200G_FN static inline
 #define B200G_SLOW static __attribute__((noinline))
@@ -50,6 +51,7 @@ namespace b200g {
 B200G_TABLE uint64_t kExpTab[256] = {B200_LIBM_EXP_TAB};        // {error term, value - (i << 45)} x 128
 B200G_TABLE uint64_t kPowLogTab[384] = {B200_LIBM_POW_TAB};     // {1/c, log(c) high, log(c) low} x 128
 B200G_TABLE uint64_t kLogTab[256] = {B200_LIBM_LOG_TAB};        // {1/c, log(c)} x 128
+B200G_TABLE uint64_t kSinCosTab[440] = {B200_LIBM_SINCOS_TAB};  // {sin, sin low, cos, cos low}(k/128) x 110
 
 static const uint64_t kInfBits = 0x7ff0000000000000ull;
 static const uint64_t kOneBits = 0x3ff0000000000000ull;
@@ -307,6 +309,110 @@ B200G_FN double cosh(double x) {
     }
     if (ix >= 0x7ff00000u) return B200G_MUL(x, x);
     return B200G_DBL(kInfBits);                            // overflow
+}
+
+// ---- sin / cos: sysdeps/ieee754/dbl-64/s_sin.c (__sin, __cos; IBM Accurate Mathematical Library),
+// FMA variants.  |x| < 105414350 is restated; beyond that glibc reduces the argument with a
+// 1200-bit 2/pi (branred.c), which is not: CUDA's sin/cos take those arguments (<= 1-2 ulp).
+B200G_FN double sc_copysign(double mag, double sgn) {
+    return B200G_DBL((B200G_BITS(mag) & ~kSignBit) | (B200G_BITS(sgn) & kSignBit));
+}
+// sin(a + dx) for |a| < ~0.86 (do_sin): odd Taylor polynomial below 0.126, else
+// sin(x0 + x) = sin x0 cos x + cos x0 sin x with x0 = a rounded to 1/128 from the table
+B200G_FN double sc_do_sin(double a, double dx) {
+    const double aa = B200G_DBL(B200G_BITS(a) & ~kSignBit);
+    if (aa < 0.126) {
+        const double xx = B200G_MUL(a, a);
+        double p = B200G_FMA(xx, -0x1.addffc2fcdf59p-26, 0x1.71de27b9a7ed9p-19);
+        p = B200G_FMA(xx, p, -0x1.a01a019db08b8p-13);
+        p = B200G_FMA(xx, p, 0x1.1111111110ecep-7);
+        p = B200G_FMA(xx, p, -0x1.5555555555555p-3);
+        const double t = B200G_FMA(xx, B200G_FMA(p, a, -B200G_MUL(dx, 0.5)), dx);
+        return B200G_ADD(a, t);
+    }
+    if (!(a > 0.0)) dx = -dx;
+    const double u = B200G_ADD(aa, 0x1.8p45);
+    const double x = B200G_SUB(aa, B200G_SUB(u, 0x1.8p45));
+    const uint32_t k = (uint32_t)B200G_BITS(u) << 2;
+    const double xx = B200G_MUL(x, x);
+    const double p = B200G_FMA(xx, 0x1.11110e829872fp-7, -0x1.5555555555515p-3);
+    const double s = B200G_ADD(x, B200G_FMA(B200G_MUL(x, xx), p, dx));
+    const double c0 = B200G_FMA(xx, B200G_FMA(xx, 0x1.6c16bedd9e239p-10, -0x1.5555555555535p-5), 0.5);
+    const double c = B200G_FMA(dx, x, B200G_MUL(xx, c0));
+    const double sn = B200G_DBL(kSinCosTab[k]), ssn = B200G_DBL(kSinCosTab[k + 1]);
+    const double cs = B200G_DBL(kSinCosTab[k + 2]), ccs = B200G_DBL(kSinCosTab[k + 3]);
+    const double cor = B200G_FMA(s, cs, B200G_FMA(-c, sn, B200G_FMA(s, ccs, ssn)));
+    return sc_copysign(B200G_ADD(sn, cor), a);
+}
+// cos(a + dx) for |a| < ~0.86 (do_cos)
+B200G_FN double sc_do_cos(double a, double dx) {
+    const double aa = B200G_DBL(B200G_BITS(a) & ~kSignBit);
+    if (a < 0.0) dx = -dx;
+    const double u = B200G_ADD(aa, 0x1.8p45);
+    const double x = B200G_ADD(B200G_SUB(aa, B200G_SUB(u, 0x1.8p45)), dx);
+    const uint32_t k = (uint32_t)B200G_BITS(u) << 2;
+    const double xx = B200G_MUL(x, x);
+    const double p = B200G_FMA(xx, 0x1.11110e829872fp-7, -0x1.5555555555515p-3);
+    const double s = B200G_FMA(B200G_MUL(x, xx), p, x);
+    const double c0 = B200G_FMA(xx, B200G_FMA(xx, 0x1.6c16bedd9e239p-10, -0x1.5555555555535p-5), 0.5);
+    const double c = B200G_MUL(xx, c0);
+    const double sn = B200G_DBL(kSinCosTab[k]), ssn = B200G_DBL(kSinCosTab[k + 1]);
+    const double cs = B200G_DBL(kSinCosTab[k + 2]), ccs = B200G_DBL(kSinCosTab[k + 3]);
+    const double cor = B200G_FMA(-s, sn, B200G_FMA(-c, cs, B200G_FMA(-s, ssn, ccs)));
+    return B200G_ADD(cs, cor);
+}
+// x = n pi/2 + (a + da), |a| <= pi/4, for |x| < 105414350 (reduce_sincos: pi/2 in four pieces)
+B200G_FN int sc_reduce(double x, double& a, double& da) {
+    const double t = B200G_FMA(x, 0x1.45f306dc9c883p-1, 0x1.8p52);
+    const double xn = B200G_SUB(t, 0x1.8p52);
+    const int n = (int)((uint32_t)B200G_BITS(t) & 3u);
+    const double y = B200G_FMA(-xn, -0x1.dde973c000000p-27, B200G_FMA(-xn, 0x1.921fb58000000p+0, x));
+    const double pp3 = -0x1.cb3b398000000p-55, pp4 = -0x1.d747f23e32ed7p-83;
+    const double t2 = B200G_FMA(-xn, pp3, y);
+    double db = B200G_FMA(-pp3, xn, B200G_SUB(y, t2));
+    const double b = B200G_FMA(-xn, pp4, t2);
+    db = B200G_ADD(db, B200G_FMA(-xn, pp4, B200G_SUB(t2, b)));
+    a = b;
+    da = db;
+    return n;
+}
+B200G_FN double sc_quadrant(double a, double da, int n) {
+    const double r = (n & 1) ? sc_do_cos(a, da) : sc_do_sin(a, da);
+    return (n & 2) ? -r : r;
+}
+B200G_FN double sin(double x) {
+    const uint32_t k = (uint32_t)(B200G_BITS(x) >> 32) & 0x7fffffffu;
+    if (k < 0x3e500000u) return x;                         // |x| < 2^-26
+    if (k < 0x3feb6000u) return sc_do_sin(x, 0.0);         // |x| < 0.855469
+    if (k < 0x400368fdu) {                                 // |x| < 2.426265: cos(pi/2 - |x|)
+        const double t = B200G_SUB(0x1.921fb54442d18p+0, B200G_DBL(B200G_BITS(x) & ~kSignBit));
+        return sc_copysign(sc_do_cos(t, 0x1.1a62633145c07p-54), x);
+    }
+    if (k < 0x419921fbu) {                                 // |x| < 105414350
+        double a, da;
+        const int n = sc_reduce(x, a, da);
+        return sc_quadrant(a, da, n);
+    }
+    if (k < 0x7ff00000u) return ::sin(x);                  // not restated (see above)
+    return B200G_DIV(x, x);                                // inf, nan
+}
+B200G_FN double cos(double x) {
+    const uint32_t k = (uint32_t)(B200G_BITS(x) >> 32) & 0x7fffffffu;
+    if (k < 0x3e400000u) return 1.0;                       // |x| < 2^-27
+    if (k < 0x3feb6000u) return sc_do_cos(x, 0.0);
+    if (k < 0x400368fdu) {                                 // sin(pi/2 - |x|)
+        const double y = B200G_SUB(0x1.921fb54442d18p+0, B200G_DBL(B200G_BITS(x) & ~kSignBit));
+        const double a = B200G_ADD(y, 0x1.1a62633145c07p-54);
+        const double da = B200G_ADD(B200G_SUB(y, a), 0x1.1a62633145c07p-54);
+        return sc_do_sin(a, da);
+    }
+    if (k < 0x419921fbu) {
+        double a, da;
+        const int n = sc_reduce(x, a, da);
+        return sc_quadrant(a, da, n + 1);
+    }
+    if (k < 0x7ff00000u) return ::cos(x);
+    return B200G_DIV(x, x);
 }
 
 // ---- pow: sysdeps/ieee754/dbl-64/e_pow.c (__pow), FMA variant ---------------------------------

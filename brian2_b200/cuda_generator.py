@@ -231,10 +231,11 @@ class CUDANodeRenderer(CPPNodeRenderer):
 
     # exp/expm1 -> constant-bank versions of the same algorithms (csrc/b200_functions.cuh);
     # on the host (hoisted loop-invariant scalars) they are the libm functions.  log, tanh, sinh,
-    # cosh are CUDA's; all of them (and pow) become glibc's arithmetic with
+    # cosh, sin, cos are CUDA's; all of them (and pow) become glibc's arithmetic with
     # prefs.devices.b200.libm = 'glibc'
     _DEVICE_MATH = {"exp": "_b200_exp", "expm1": "_b200_expm1", "log": "_b200_log",
-                    "tanh": "_b200_tanh", "sinh": "_b200_sinh", "cosh": "_b200_cosh"}
+                    "tanh": "_b200_tanh", "sinh": "_b200_sinh", "cosh": "_b200_cosh",
+                    "sin": "_b200_sin", "cos": "_b200_cos"}
 
     def render_func(self, node):
         return self._DEVICE_MATH.get(node.id, super().render_func(node))

@@ -7,7 +7,8 @@ the arithmetic of the host's libm (csrc/b200_glibc_math.cuh), so that state vari
 bit-identical to a ``cpp_standalone`` run -- the oracle of this path.
 glibc >= 2.28 computes exp/pow/log from small tables (``__exp_data``: 2^(i/128) as value + error
 term; ``__pow_log_data``: 1/c, log(c) in two pieces for 128 subintervals of [0.71, 1.42);
-``__log_data``: 1/c, log(c) for 128 subintervals of [0.69, 1.38)) whose
+``__log_data``: 1/c, log(c) for 128 subintervals of [0.69, 1.38); sin/cos use ``__sincostab``:
+sin and cos of k/128 in two pieces) whose
 entries were chosen by a search, not by a closed formula, so they cannot be recomputed here: they
 are looked up in the ``.rodata`` of the very library the oracle calls, by content (each table
 follows a run of constants with known values), checked structurally, and written into the
@@ -111,7 +112,8 @@ def read_tables(path=None):
     Returns a dict: ``exp_k`` (InvLn2N, Shift, NegLn2hiN, NegLn2loN, C2..C5 as doubles), ``exp_tab``
     (256 uint64: error term, scaled value per entry), ``pow_k`` (Ln2hi, Ln2lo, A0..A6), ``pow_tab``
     (128 x (invc, logc, logctail) as uint64), ``log_k`` (Ln2hi, Ln2lo, A0..A4, B0..B10), ``log_tab``
-    (128 x (invc, logc) as uint64), ``path``.
+    (128 x (invc, logc) as uint64), ``sincos_tab`` (110 x (sin high, low, cos high, low) as uint64),
+    ``path``.
     """
     path = path or find_libm()
     data, _ = _rodata(path)
@@ -178,8 +180,17 @@ def read_tables(path=None):
         if not (0.68 < invc < 1.46 and abs(logc + math.log(invc)) < 1e-13):
             raise RuntimeError(f"libm: log table entry {i} fails its check")
         log_tab += u64(ltab + 16 * i, 2)
+
+    # ---- __sincostab: {sin(k/128) high, low, cos(k/128) high, low} for k = 0..109 --------------
+    sbase = _find_run(data, [0.0, 0.0, 1.0, 0.0, float.fromhex("0x1.fffeaaaaeeeefp-8")], "sin/cos table")
+    sincos_tab = u64(sbase, 440)
+    for k in range(110):
+        sn, ssn, cs, ccs = f64(sbase + 32 * k, 4)
+        if not (abs(sn - math.sin(k / 128)) < 2e-16 and abs(cs - math.cos(k / 128)) < 2e-16
+                and abs(ssn) < 2.0 ** -53 and abs(ccs) < 2.0 ** -53):
+            raise RuntimeError(f"libm: sin/cos table entry {k} fails its check")
     return {"exp_k": exp_k, "exp_tab": exp_tab, "pow_k": pow_k, "pow_tab": pow_tab,
-            "log_k": log_k, "log_tab": log_tab, "path": path}
+            "log_k": log_k, "log_tab": log_tab, "sincos_tab": sincos_tab, "path": path}
 
 
 def header_text(tables=None):
@@ -193,7 +204,7 @@ def header_text(tables=None):
     names_l = ["LN2HI", "LN2LO"] + [f"A{i}" for i in range(5)] + [f"B{i}" for i in range(11)]
     lines = [
         "// b200_libm_tables.h -- generated by brian2_b200/libm_tables.py from",
-        f"// {t['path']}: the constants and tables of the host libm's exp()/pow()/log(),",
+        f"// {t['path']}: the constants and tables of the host libm's exp()/pow()/log()/sin()/cos(),",
         "// so that device code reproduces the arithmetic of the oracle's own library.",
         "#pragma once",
     ]
@@ -201,6 +212,7 @@ def header_text(tables=None):
     lines += [f"#define B200_LIBM_POW_{n} {hexd(v)}" for n, v in zip(names_p, t["pow_k"])]
     lines += [f"#define B200_LIBM_LOG_{n} {hexd(v)}" for n, v in zip(names_l, t["log_k"])]
     lines.append("#define B200_LIBM_LOG_TAB \\\n    " + rows(t["log_tab"]))
+    lines.append("#define B200_LIBM_SINCOS_TAB \\\n    " + rows(t["sincos_tab"]))
     lines.append("#define B200_LIBM_EXP_TAB \\\n    " + rows(t["exp_tab"]))
     lines.append("#define B200_LIBM_POW_TAB \\\n    " + rows(t["pow_tab"]))
     return "\n".join(lines) + "\n"

@@ -121,6 +121,30 @@ int main(int argc, char** argv) {
         sweep1("cosh any bit pattern", n / 2, [] { return anybits(); }, my_cosh, r_cosh);
     }
 
+    {
+        double (*volatile ref_sin)(double) = ::sin;
+        double (*volatile ref_cos)(double) = ::cos;
+        auto r_sin = [&](double x) { return ref_sin(x); };
+        auto r_cos = [&](double x) { return ref_cos(x); };
+        auto my_sin = [](double x) { return b200g::sin(x); };
+        auto my_cos = [](double x) { return b200g::cos(x); };
+        auto mags = [] { return uni(-1, 1) * std::ldexp(1.0, (int)(rnd() % 90) - 62); };     // 2^-62 .. 2^27
+        sweep1("sin  [-0.9, 0.9]", n, [] { return uni(-0.9, 0.9); }, my_sin, r_sin);
+        sweep1("sin  [-2.5, 2.5]", n, [] { return uni(-2.5, 2.5); }, my_sin, r_sin);
+        sweep1("sin  [-100, 100]", n, [] { return uni(-100, 100); }, my_sin, r_sin);
+        sweep1("sin  [-1e8, 1e8]", n, [] { return uni(-1.05e8, 1.05e8); }, my_sin, r_sin);
+        sweep1("sin  all magnitudes", n, mags, my_sin, r_sin);
+        sweep1("sin  near multiples of pi/2", n / 2, [] {
+            return (double)((long)(rnd() % 2000000) - 1000000) * 1.5707963267948966 + uni(-1e-6, 1e-6); }, my_sin, r_sin);
+        sweep1("cos  [-0.9, 0.9]", n, [] { return uni(-0.9, 0.9); }, my_cos, r_cos);
+        sweep1("cos  [-2.5, 2.5]", n, [] { return uni(-2.5, 2.5); }, my_cos, r_cos);
+        sweep1("cos  [-100, 100]", n, [] { return uni(-100, 100); }, my_cos, r_cos);
+        sweep1("cos  [-1e8, 1e8]", n, [] { return uni(-1.05e8, 1.05e8); }, my_cos, r_cos);
+        sweep1("cos  all magnitudes", n, mags, my_cos, r_cos);
+        sweep1("cos  near multiples of pi/2", n / 2, [] {
+            return (double)((long)(rnd() % 2000000) - 1000000) * 1.5707963267948966 + uni(-1e-6, 1e-6); }, my_cos, r_cos);
+    }
+
     sweep2("pow  gate**{3,4}", n, [](double& x, double& y) { x = uni(0, 1); y = 3 + (double)(rnd() & 1); }, my_pow, r_pow);
     sweep2("pow  exp(a)**c (HH rates)", n, [&](double& x, double& y) {
         x = ref_exp(uni(-10, 10)); y = (rnd() & 1) ? 0.025 : 0.05555555555555555; }, my_pow, r_pow);

@@ -537,13 +537,13 @@ def poissonfn(b, N=4000, duration=0.02, seed=53):
 
 def mathfuncs(b, N=2048, duration=0.01, seed=5):
     """Every libm function the hot path calls (exp, expm1, log, pow; plus tanh,
-    sinh, cosh, which glibc builds from exp/expm1) evaluated per
+    sinh, cosh, which glibc builds from exp/expm1, and sin, cos) evaluated per
     neuron and per step in in-loop code over wide argument ranges (x in [-30, 30], p in (0, 60],
     exponents in [-6, 6]), plus the powers g++ folds at compile time (x**2, p**-1) and an integer
     power.  The arguments come from three chaotic (logistic) maps per neuron which every function
     value perturbs a little: a single result that is 1 ulp off at any step is amplified by ~2 per
     step until the whole state differs, so the final state is bit-identical to the reference's
-    cpp_standalone run only if ALL evaluations (2048 neurons x 100 steps x 12 calls) were -- which
+    cpp_standalone run only if ALL evaluations (2048 neurons x 100 steps x 14 calls) were -- which
     `prefs.devices.b200.libm = 'glibc'` promises."""
     b.seed(seed)
     G = b.NeuronGroup(N, """u : 1
@@ -562,7 +562,9 @@ def mathfuncs(b, N=2048, duration=0.01, seed=5):
                             y_mix : 1
                             y_tanh : 1
                             y_sinh : 1
-                            y_cosh : 1""", name="mf_G")
+                            y_cosh : 1
+                            y_sin : 1
+                            y_cos : 1""", name="mf_G")
     G.u = "0.05 + 0.9*rand()"
     G.w = "0.05 + 0.9*rand()"
     G.s = "0.05 + 0.9*rand()"
@@ -580,14 +582,17 @@ def mathfuncs(b, N=2048, duration=0.01, seed=5):
                        y_tanh = tanh(0.1*x)
                        y_sinh = sinh(0.2*x)
                        y_cosh = cosh(0.2*x)
+                       y_sin = sin(x*p)
+                       y_cos = cos(x*p*p)
                        u = 3.99*u*(1 - u)*(1 - 0.01*y_exp/(1 + y_exp) - 0.001*y_rel/(1 + y_rel) - 0.001*y_mix/(1 + y_mix))
                        w = 3.98*w*(1 - w)*(1 - 0.01*y_pow/(1 + y_pow) - 0.001/(1 + y_log*y_log))
-                       s = 3.97*s*(1 - s)*(1 - 0.01/(1 + y_inv) - 0.001/(1 + y_expm1*y_expm1) - 0.001*y_tanh*y_tanh - 0.001/(1 + y_sinh*y_sinh) - 0.001/y_cosh)""", name="mf_rr")
+                       s = 3.97*s*(1 - s)*(1 - 0.01/(1 + y_inv) - 0.001/(1 + y_expm1*y_expm1) - 0.001*y_tanh*y_tanh - 0.001/(1 + y_sinh*y_sinh) - 0.001/y_cosh - 0.001*y_sin*y_sin - 0.001*y_cos*y_cos)""", name="mf_rr")
     objs = dict(G=G)
     objs["net"] = b.Network(*objs.values())
     objs["duration"] = duration
     objs["state"] = [("G", v) for v in ("u", "w", "s", "x", "p", "q", "y_exp", "y_expm1", "y_rel", "y_log",
-                                        "y_pow", "y_sq", "y_inv", "y_mix", "y_tanh", "y_sinh", "y_cosh")]
+                                        "y_pow", "y_sq", "y_inv", "y_mix", "y_tanh", "y_sinh", "y_cosh",
+                                        "y_sin", "y_cos")]
     return objs
 
 

@@ -1,5 +1,5 @@
 """`prefs.devices.b200.libm = 'glibc'` (csrc/b200_glibc_math.cuh, brian2_b200/libm_tables.py):
-the device's exp / expm1 / log / pow (and tanh / sinh / cosh) must be the host glibc's functions bit for bit, because the oracle
+the device's exp / expm1 / log / pow (and tanh / sinh / cosh / sin / cos) must be the host glibc's functions bit for bit, because the oracle
 of this path -- the reference's cpp_standalone build -- calls exactly those.  Everything that can
 be checked without a GPU is checked here: the tables found in the host's libm mean what the
 algorithm assumes, the restated arithmetic (compiled for the host from the same header the device
@@ -33,6 +33,11 @@ def test_tables_of_the_host_libm_mean_what_the_algorithms_assume(tables):
 
     mp.mp.prec = 240
     assert len(tables["exp_tab"]) == 256 and len(tables["pow_tab"]) == 384 and len(tables["log_tab"]) == 256
+    for k in range(110):                 # sin/cos: value of sin(k/128), cos(k/128) as high + low
+        sn, ssn, cs, ccs = (_dbl(v) for v in tables["sincos_tab"][4 * k:4 * k + 4])
+        xk = mp.mpf(k) / 128
+        assert abs(mp.mpf(sn) + mp.mpf(ssn) - mp.sin(xk)) < mp.mpf(2) ** -100, k
+        assert abs(mp.mpf(cs) + mp.mpf(ccs) - mp.cos(xk)) < mp.mpf(2) ** -100, k
     for i in range(128):
         H = _dbl(tables["exp_tab"][2 * i + 1] + (i << 45))
         T = _dbl(tables["exp_tab"][2 * i])
@@ -58,14 +63,14 @@ def test_header_is_self_describing(tables, tmp_path):
     path = libm_tables.write_header(str(tmp_path), tables)
     text = open(path).read()
     assert tables["path"] in text and "#define B200_LIBM_EXP_TAB" in text and "#define B200_LIBM_POW_TAB" in text
-    assert len(re.findall(r"0x[0-9a-f]{16}ull", text)) == 256 + 384 + 256
+    assert len(re.findall(r"0x[0-9a-f]{16}ull", text)) == 256 + 384 + 256 + 440
     stamp = os.path.getmtime(path)
     libm_tables.write_header(str(tmp_path), tables)          # unchanged content: not rewritten (make)
     assert os.path.getmtime(path) == stamp
 
 
 def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
-    """tests/cuda/glibc_math_test.cpp: 45 argument distributions (Hodgkin-Huxley ranges, whole
+    """tests/cuda/glibc_math_test.cpp: 57 argument distributions (Hodgkin-Huxley ranges, whole
     range, over/underflow, subnormal results, random bit patterns, special values), 4 * 10^6
     arguments each (> 10^7 per function), every result compared with the libm call the
     reference's C++ code makes.  NaNs compare equal to NaNs."""
@@ -79,8 +84,8 @@ def test_restated_functions_return_the_bits_of_the_host_glibc(tables, tmp_path):
     out = subprocess.run([exe, "4000000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
     lines = [l for l in out.stdout.splitlines() if "arguments" in l]
-    assert len(lines) == 45 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
-    for fn in ("exp ", "expm1", "log ", "pow ", "tanh", "sinh", "cosh"):
+    assert len(lines) == 57 and all(l.rstrip().endswith(", 0 differ") for l in lines), out.stdout
+    for fn in ("exp ", "expm1", "log ", "pow ", "tanh", "sinh", "cosh", "sin ", "cos "):
         assert sum(int(l.split()[-4]) for l in lines if l.startswith(fn)) > 10 ** 7, fn
 
 
