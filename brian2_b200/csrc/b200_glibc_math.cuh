@@ -1,4 +1,5 @@
-// b200_glibc_math.cuh -- exp / expm1 / log / pow with the arithmetic of the host's glibc, for device code.
+// b200_glibc_math.cuh -- exp / expm1 / log / pow / tanh / sinh / cosh / sin / cos with the arithmetic of
+// the host's glibc, for device code.
 //
 // Why: the oracle of this path is the reference's cpp_standalone build, whose exp()/expm1()/log()/pow()
 // are glibc's.  CUDA's functions differ from them by <= 1 ulp in a few per cent of the arguments,
@@ -7,7 +8,8 @@
 // instead: every floating-point operation -- including which a*b+c are fused -- is the one the
 // x86-64 FMA variants of glibc 2.39 execute (`__exp_fma`, `__log_fma`, `__pow_fma`: the table-driven
 // algorithms of sysdeps/ieee754/dbl-64/e_exp.c, e_log.c, e_pow.c; `__expm1_fma`: the fdlibm algorithm of
-// s_expm1.c), so the results are bit-identical for every argument.  The three lookup tables and the
+// s_expm1.c; further down tanh/sinh/cosh and sin/cos), so the results are bit-identical for every
+// argument (sin/cos: |x| < 1.05e8).  The four lookup tables and the
 // polynomial coefficients come from the host's libm itself (b200_libm_tables.h, written into the
 // project by brian2_b200/libm_tables.py).  tests/cuda/glibc_math_test.cpp compiles this header for
 // the host and compares it with the real functions over >= 10^7 arguments per function.

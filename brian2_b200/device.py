@@ -116,8 +116,8 @@ prefs.register_preferences(
         default="cuda",
         validator=lambda v: v in ("cuda", "glibc"),
         docs="""
-        Arithmetic of ``exp``, ``expm1`` (``exprel``), ``log``, ``pow``, ``tanh``, ``sinh`` and ``cosh`` in
-        double-precision device code.
+        Arithmetic of ``exp``, ``expm1`` (``exprel``), ``log``, ``pow``, ``tanh``, ``sinh``, ``cosh``,
+        ``sin`` and ``cos`` in double-precision device code.
         ``'cuda'``: CUDA's algorithms (<= 1 ulp from the host's glibc; state variables of a
         Hodgkin-Huxley network agree with ``cpp_standalone`` to rtol 1e-9, spikes are identical).
         ``'glibc'``: the algorithms of the host's glibc, operation by operation, with the lookup
