@@ -139,3 +139,24 @@ def test_hodgkin_huxley_project_builds_with_glibc_math(brian):
     with pytest.raises(Exception):
         b.prefs["devices.b200.libm"] = "fdlibm"
     assert b.prefs["devices.b200.libm"] == "cuda"
+
+
+def test_generated_code_routes_every_libm_call_through_the_switchable_wrappers(brian):
+    """Code generation only (tests/models.py: mathfuncs): every transcendental function of the
+    in-loop code is rendered as its `_b200_*` wrapper (csrc/b200_functions.cuh), which is CUDA's
+    function by default and glibc's arithmetic under -DB200_GLIBC_MATH; powers go through
+    `_brian_pow`, `exp(a)**c` through `_b200_exp_pow`."""
+    import __graft_entry__ as ge
+
+    directory, _ = ge.build_project("mathfuncs", directory=os.path.join(ge.PREBUILT, "plan_mathfuncs"),
+                                    compile=False, prefs_update={"devices.b200.libm": "glibc"})
+    code = open(os.path.join(directory, "code_objects", "mf_rr_codeobject.cuh")).read()
+    for call in ("_b200_exp(x)", "_b200_expm1(0.1 * x)", "_exprel(0.05 * x)", "_b200_log(p)", "_brian_pow(p, q)",
+                 "_brian_pow(x, 2)", "_brian_pow(p, - 1)", "_brian_pow(w, 3)", "_b200_exp_pow(0.01 * x, 0.3)",
+                 "_b200_tanh(0.1 * x)", "_b200_sinh(0.2 * x)", "_b200_cosh(0.2 * x)", "_b200_sin(x * p)",
+                 "_b200_cos((x * p) * p)"):
+        assert call in code, call
+    assert not re.search(r"[^_a-z0-9](exp|expm1|log|sin|cos|tanh|sinh|cosh|pow)\(", code)
+    functions = open(os.path.join(ROOT, "brian2_b200", "csrc", "b200_functions.cuh")).read()
+    for fn in ("exp", "expm1", "log", "pow", "tanh", "sinh", "cosh", "sin", "cos"):
+        assert f"b200g::{fn}(" in functions or f"B200_LIBM_WRAPPER({fn})" in functions, fn
