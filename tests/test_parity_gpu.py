@@ -118,7 +118,7 @@ def _run_with_glibc_math(brian, project_dir, case):
 
 
 def test_cobahh_state_bit_exact_with_glibc_math(brian, project_dir):
-    """`prefs.devices.b200.libm = 'glibc'`: exp / expm1 / pow of the device are glibc's algorithms
+    """`prefs.devices.b200.libm = 'glibc'`: exp / expm1 / pow (...) of the device are glibc's algorithms
     operation by operation (csrc/b200_glibc_math.cuh; bit-identity of the functions themselves:
     tests/test_glibc_math_cpu.py), so the Hodgkin-Huxley network is no longer "within rtol 1e-9":
     every state variable of every neuron, the recorded voltage traces and the spike train are
@@ -128,10 +128,11 @@ def test_cobahh_state_bit_exact_with_glibc_math(brian, project_dir):
 
 
 def test_every_libm_call_bit_exact_with_glibc_math(brian, project_dir):
-    """exp, expm1, exprel, log, pow with run-time and literal exponents (incl. the ones g++ folds:
-    x**2, p**-1) and exp(a)**c, 4096 neurons x 100 steps, arguments over [-30, 30] / (0, 60] /
-    [-6, 6] from chaotic maps that every result perturbs (tests/models.py: mathfuncs): the final
-    state equals the reference's bit for bit only if every single evaluation on the device did."""
+    """exp, expm1, exprel, log, tanh, sinh, cosh, sin, cos, pow with run-time and literal exponents
+    (incl. the ones g++ folds: x**2, p**-1) and exp(a)**c, 2048 neurons x 100 steps, arguments over
+    [-30, 30] / (0, 60] / [-6, 6] (sin/cos: up to 1e5) from chaotic maps that every result perturbs
+    (tests/models.py: mathfuncs): the final state equals the reference's bit for bit only if every
+    single evaluation on the device did."""
     objs, res = _run_with_glibc_math(brian, project_dir, "mathfuncs")
     gold = np.load(os.path.join(GOLDEN, "mathfuncs.npz"))
     for key in gold.files:
