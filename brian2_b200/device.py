@@ -1251,6 +1251,10 @@ class B200Device(CPPStandaloneDevice):
             flags.append("-DB200_CSR_EVICT_LAST")
         if prefs.devices.b200.libm == "glibc":
             flags.append("-DB200_GLIBC_MATH")
+            if prefs.devices.b200.fmad:
+                logger.warn("devices.b200.libm = 'glibc' makes the libm calls bit-identical to cpp_standalone, "
+                            "but devices.b200.fmad = True lets nvcc fuse the a*b+c of the generated code: "
+                            "state variables will not be bit-identical.", name_suffix="glibc_fmad", once=True)
         return " ".join(flags)
 
     def generate_makefile(self, writer, compiler, compiler_flags, linker_flags, nb_threads, debug):
